@@ -1,0 +1,24 @@
+"""CPU oracle for the TweedieMix fusion-sampling hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``tweediemix_b200/`` imports this
+package; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` do, and there only as the checker or
+the timed CPU baseline, never as the shipped path.
+
+Parity pinning:
+  * the reference ships no tests and no golden vectors, and its
+    sampler cannot be imported here (diffusers/xformers absent), so the
+    sampler-level restatement (``step_math``, ``sampler_ref``) is pinned only
+    by the schedule table in SURVEY App. C and by hand-derived known answers:
+    **parity unpinned** for those two modules;
+  * the hook restatement (``hooks_ref``) IS pinned: the reference's own
+    ``fusion_generation/utils_custom.py`` and ``utils_lora.py`` import and run
+    in the build container, and ``tests/golden/make_golden.py`` records their
+    outputs on seeded inputs into ``tests/golden/*.pt``; ``tests/test_oracle_hooks.py``
+    replays them bit-for-bit against ``hooks_ref``.
+
+Every function cites the reference file:line it follows (paths relative to the
+reference checkout, e.g. ``fusion_generation/fusion_sampling.py:305-307``).
+Lines marked [D] restate diffusers==0.29.2 (``requirements.txt:4``), which is
+not vendored in the reference and not installed in this image.
+"""
