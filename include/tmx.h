@@ -1,0 +1,168 @@
+/* tmx.h — C ABI of libtmx.so: the B200 (sm_100a) kernels behind the TweedieMix fusion-sampling
+ * hot path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference (KwonGihyun/TweedieMix) is pure Python with no FFI of its own; each entry point
+ * below replaces the arithmetic of a specific span of reference code (cited per function, paths
+ * relative to the reference checkout; [D] = diffusers 0.29.2, the reference's pinned dependency).
+ * INTEGRATION.md shows the ctypes stubs a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; kernels never allocate, free or
+ *     retain pointers past return; workspaces are passed explicitly (tmx_*_workspace_bytes);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does no host
+ *     sync and is CUDA-graph capturable once tmx_init(device) has run;
+ *   - return value 0 = success, negative TMX_E* = failure; tmx_last_error() gives a thread-local
+ *     message.  There is NO CPU fallback: an unsupported shape/dtype/arch is an error.
+ */
+#ifndef TMX_H
+#define TMX_H
+
+#if defined(__GNUC__)
+#define TMX_API __attribute__((visibility("default")))
+#else
+#define TMX_API
+#endif
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMX_VERSION 100            /* 0.1.0 */
+
+/* element types */
+#define TMX_F32  0
+#define TMX_F16  1
+#define TMX_BF16 2
+
+/* error codes */
+#define TMX_OK          0
+#define TMX_EINVAL     -1          /* bad argument (null pointer, non-positive size, ...) */
+#define TMX_ESHAPE     -2          /* shape not supported by the kernel */
+#define TMX_EDTYPE     -3          /* dtype not supported */
+#define TMX_EALIGN     -4          /* pointer / stride not aligned as required */
+#define TMX_EARCH      -5          /* device is not sm_100 */
+#define TMX_ECUDA      -6          /* CUDA runtime / driver error (message in tmx_last_error) */
+#define TMX_ENOINIT    -7          /* tmx_init(device) was not called for the current device */
+
+/* activation for tmx_groupnorm_fwd */
+#define TMX_ACT_NONE 0
+#define TMX_ACT_SILU 1
+
+/* memory layout for tmx_groupnorm_fwd */
+#define TMX_NCHW 0
+#define TMX_NHWC 1
+
+/* rounding mode for the blend kernels */
+#define TMX_ROUND_FP32 0           /* all arithmetic in fp32 on the loaded eps */
+#define TMX_ROUND_REF  1           /* re-round intermediates to eps' dtype exactly where the
+                                      reference's PyTorch type promotion does */
+
+TMX_API int         tmx_version(void);
+TMX_API const char* tmx_last_error(void);
+
+/* One-time per-device setup (function attributes, SM count, driver entry points).
+ * Must be called outside stream capture.  Idempotent. */
+TMX_API int tmx_init(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * k7 — fused CFG combine + Tweedie x0 + mask-weighted concept blend + DDIM update.
+ * Replaces fusion_generation/fusion_sampling.py:376-386,430,471-472 (fused phase) and, through
+ * `weights`/null `masks`, :392-403 (resampling x0), :407-412 (re-noise), :421-430 (plain CFG),
+ * :441-447 (jump).
+ *
+ *   eps_u      = eps[img][0]
+ *   eps_c      = eps_u + g * (eps[img][1+c] - eps_u)                       c = 0..K-1
+ *   x0         = sum_c  w_c * m_c(p) * (x - sqrt(1-a_t) * eps_c) / sqrt(a_t)
+ *   x_out      = is_last ? x0 : sqrt(a_next) * x0 + sqrt(1-a_next) * eps_u
+ *
+ * x, x_out, x0_out : fp32 [imgs, C, HW]            (x_out may alias x; x0_out may be NULL)
+ * eps              : eps_dtype [imgs, K+1, C, HW]
+ * masks            : fp32 [K, HW] shared by all images, or NULL (= all ones)
+ * weights          : HOST pointer to K floats, or NULL (= all ones)
+ * Requires HW % 8 == 0 and 16-byte aligned pointers.
+ * Algorithmic bytes per image: C*HW*(4+4) + (K+1)*C*HW*sizeof(eps) + K*HW*4  (+ C*HW*4 if x0_out).
+ */
+TMX_API int tmx_tweedie_blend_ddim_fwd(const float* x, const void* eps, const float* masks,
+                               const float* weights, float* x_out, float* x0_out,
+                               int imgs, int K, int C, int HW,
+                               float a_t, float a_next, float g, int is_last,
+                               int eps_dtype, int round_mode, void* stream);
+
+/* Concept-parallel (multi-GPU) split of k7, SURVEY §8e.  Linear form
+ *   x0 = [ M x - s (1-g) M eps_u - s g sum_c m_c eps_c ] / sqrt(a_t),  M = sum_c m_c, s = sqrt(1-a_t)
+ * partial: acc[img][0] (+)= sum_{rows r>0 owned} m_{c(r)} * eps_r ; acc[img][1] = eps_u if the
+ *          uncond row is owned else 0.  acc is fp32 [imgs, 2, C, HW] and is what gets all-reduced.
+ * finish : consumes the all-reduced acc and produces x_out / x0_out on every rank identically.
+ * eps_rows : eps_dtype [imgs, R, C, HW] — only the R rows this rank computed;
+ * row_ids  : HOST int[R], global row index of each local row (0 = uncond, 1+c = concept c).
+ */
+TMX_API int tmx_blend_partial_fwd(const void* eps_rows, const float* masks, const int* row_ids,
+                          float* acc, int imgs, int R, int K, int C, int HW,
+                          int eps_dtype, void* stream);
+TMX_API int tmx_blend_finish_fwd(const float* x, const float* acc, const float* masks,
+                         float* x_out, float* x0_out, int imgs, int K, int C, int HW,
+                         float a_t, float a_next, float g, int is_last, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * k4 / k5 — GroupNorm (+ optional per-(n,c) additive bias before the norm, + optional SiLU).
+ * Replaces [D] ResnetBlock2D's  norm1 -> SiLU,  (+temb) -> norm2 -> SiLU  (body mirrored in the
+ * reference at video_gen/utils_attn.py:391-431), conv_norm_out -> SiLU, and Transformer2DModel.norm.
+ *
+ *   y = act( (x + add[n,c] - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c] )
+ *
+ * x, y      : dtype [N, C, HW] (TMX_NCHW) or [N, HW, C] (TMX_NHWC); y may alias x
+ * gamma/beta: fp32 [C];  add: fp32 [N, C] or NULL
+ * workspace : tmx_groupnorm_workspace_bytes(N, C, HW, G, layout) bytes, 16-byte aligned
+ * Statistics in fp32 (Chan/Welford merge, deterministic), one rounding on store.
+ * Requires C % G == 0, C % 8 == 0 (NHWC) or HW*(C/G) % 8 == 0 (NCHW).
+ * Algorithmic bytes: 2 * N*C*HW * sizeof(dtype).
+ */
+TMX_API size_t tmx_groupnorm_workspace_bytes(int N, int C, int HW, int G, int layout);
+TMX_API int    tmx_groupnorm_fwd(const void* x, const float* gamma, const float* beta, const float* add,
+                         void* y, void* workspace, int N, int C, int HW, int G, float eps,
+                         int act, int layout, int dtype, void* stream);
+
+/* k6 — residual add:  y = (a + b) * inv_scale    ([D] ResnetBlock2D tail, output_scale_factor;
+ * also the three residual adds of BasicTransformerBlock).  n elements, n % 8 == 0; y may alias. */
+TMX_API int tmx_resadd_fwd(const void* a, const void* b, void* y, size_t n, float inv_scale,
+                   int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * k1 / k2 — scaled-dot-product attention forward, head dim 64, no mask, non-causal:
+ *   O[b,i,h,:] = softmax_j( scale * Q[b,i,h,:] . K[b,j,h,:] ) V[b,j,h,:]
+ * tcgen05.mma (kind::f16) with fp32 accumulators in TMEM, operands staged by TMA.
+ * Replaces the einsum/softmax/einsum of fusion_generation/utils_custom.py:91-105 and
+ * utils_lora.py:99-113 (and the xformers call diffusers makes for attn1 in the custom variant).
+ *
+ * q, o : dtype [B, Nq, H, 64]; k, v : dtype [B, Nk, H, 64] — i.e. diffusers' [B, N, H*D] tensors
+ * before head_to_batch_dim, so no permute is needed on either side.  Row strides (elements)
+ * between consecutive tokens are given explicitly so that q/k/v may be slices of a fused QKV
+ * projection output: *_stride_n >= H*64, multiple of 8; batch stride = N * stride_n.
+ * dtype TMX_F16 or TMX_BF16.  Nq, Nk >= 1 (tails are masked).
+ * Algorithmic FLOPs: 4 * B * H * Nq * Nk * 64.
+ */
+TMX_API int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o,
+                 int B, int H, int Nq, int Nk, int D,
+                 int64_t q_stride_n, int64_t k_stride_n, int64_t v_stride_n, int64_t o_stride_n,
+                 float scale, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * k3 — per-row routed projection (grouped GEMM over batch rows, one weight matrix per row):
+ *   y[b] = x[b] @ W[b]^T (+ (x[b] @ down[b]^T) @ up[b]^T)          b = 0..B-1
+ * Replaces the per-row nn.Linear + torch.cat of utils_custom.py:64-82 (concept K/V weights) and
+ * the rank-r LoRA deltas of utils_lora.py:65-79,113-119 / model_lora.py:41-48.
+ * x : dtype [B, M, Kin];  w : HOST array of B device pointers to dtype [Nout, Kin];
+ * lora_down / lora_up : HOST arrays of B device pointers ([r, Kin] / [Nout, r]) or NULL entries
+ * (NULL array = no LoRA anywhere);  y : dtype [B, M, Nout].
+ */
+TMX_API int tmx_routed_linear_fwd(const void* x, const void* const* w, const void* const* lora_down,
+                          const void* const* lora_up, void* y, int B, int M, int Kin, int Nout,
+                          int rank, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMX_H */

@@ -1,0 +1,195 @@
+"""-m gpu: parity of the bandwidth kernels (k4/k5 GroupNorm+SiLU, k6 residual add, k7 fused
+CFG/Tweedie/blend/DDIM) against the CPU oracle, through the C ABI.
+
+Tolerances (stated per test):
+  k7, TMX_ROUND_REF : <= 4 fp32 ulp of the oracle evaluated with the same eps dtype (the kernel
+                      re-rounds exactly where torch's promotion does; torch-CUDA divides by
+                      multiplying with a reciprocal, the CPU oracle and the kernel divide)
+  k7, TMX_ROUND_FP32: 2e-5 relative vs the fp32 oracle on upcast eps
+  GroupNorm         : fp32 I/O 3e-5 abs; 16-bit I/O one rounding of the output dtype
+  residual add      : exact for fp32, one output rounding for 16-bit
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import step_math as sm
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def ops():
+    from tweediemix_b200 import build, ops as o
+    build.build()
+    return o
+
+
+DTYPES = [torch.float16, torch.bfloat16, torch.float32]
+
+
+def _blend_inputs(K, h, w, dtype, seed, imgs=1):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(imgs, 4, h, w, generator=g)
+    eps = torch.randn(imgs, K + 1, 4, h, w, generator=g).to(dtype)
+    return x, eps
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("K,hw", [(3, (128, 128)), (3, (32, 32)), (8, (128, 128)), (1, (16, 8))])
+def test_blend_ref_rounding_matches_oracle(dtype, K, hw):
+    o = ops()
+    h, w = hw
+    masks = synth.fixture_masks(h, w) if K == 3 else synth.stripe_masks(K, h, w)
+    x, eps = _blend_inputs(K, h, w, dtype, 11)
+    for (at, an, last) in [(0.043827, 0.051787, False), (0.005844, 0.007365, False), (0.99915, 0.99915, True)]:
+        want, want0 = sm.fused_step(x, eps[0], masks, at, an, 0.8, is_last=last)
+        x0 = torch.empty_like(x).cuda()
+        got = o.tweedie_blend_ddim(x.cuda(), eps.cuda(), masks.cuda(), at, an, 0.8, is_last=last,
+                                   x0_out=x0, ref_rounding=True).cpu()
+        scale = want.abs().max().item()
+        assert (got - want).abs().max().item() <= 4 * 1.2e-7 * max(scale, 1.0) * 8, (dtype, K, at)
+        torch.testing.assert_close(x0.cpu(), want0, rtol=2e-6, atol=2e-6 * max(scale, 1.0))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_blend_fp32_mode_and_batched_images(dtype):
+    o = ops()
+    K, h, w, imgs = 3, 64, 64, 5
+    masks = synth.fixture_masks(h, w)
+    x, eps = _blend_inputs(K, h, w, dtype, 12, imgs)
+    got = o.tweedie_blend_ddim(x.cuda(), eps.cuda(), masks.cuda(), 0.3, 0.4, 0.8).cpu()
+    for i in range(imgs):
+        want, _ = sm.fused_step(x[i:i + 1], eps[i].float(), masks, 0.3, 0.4, 0.8)
+        torch.testing.assert_close(got[i:i + 1], want, rtol=2e-5, atol=2e-5)
+
+
+def test_blend_weight_and_nullmask_forms():
+    """resampling x0 (:392-403), plain CFG (:425-430) and re-noise (:407-412) through the same kernel."""
+    o = ops()
+    K, h, w = 3, 32, 32
+    x, eps = _blend_inputs(K, h, w, torch.float32, 13)
+    at, an, g = 0.0058, 0.0074, 0.8
+    # resample: rows [uncond, multi, single_1, single_2]; weights [K-1, -1, -1]
+    x0 = torch.empty_like(x).cuda()
+    got = o.tweedie_blend_ddim(x.cuda(), eps.cuda(), None, at, an, g, weights=[K - 1, -1, -1], x0_out=x0).cpu()
+    want0 = sm.resample_x0(x, eps[0], at, g, K)
+    torch.testing.assert_close(x0.cpu(), want0, rtol=2e-5, atol=2e-4)
+    torch.testing.assert_close(got, sm.ddim_update(want0, eps[0, :1], an), rtol=2e-5, atol=2e-4)
+    # plain CFG
+    got = o.tweedie_blend_ddim(x.cuda(), eps[:, :2].contiguous().cuda(), None, at, an, g).cpu()
+    want, _ = sm.cfg_step(x, eps[0, :2], at, an, g)
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-4)
+    # re-noise = CFG step with the alphas swapped
+    got = o.tweedie_blend_ddim(x.cuda(), eps[:, :2].contiguous().cuda(), None, an, at, g).cpu()
+    torch.testing.assert_close(got, sm.renoise(x, eps[0, :2], at, an, g), rtol=2e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_blend_partial_finish_equals_fused(dtype):
+    """Concept-parallel split: any assignment of rows to 'ranks' sums to the fused result."""
+    o = ops()
+    K, h, w = 5, 32, 32
+    g_ = torch.Generator().manual_seed(3)
+    masks = (torch.rand(K, 1, h, w, generator=g_) > 0.4).float()
+    x, eps = _blend_inputs(K, h, w, dtype, 14)
+    want, want0 = sm.fused_step(x, eps[0].float(), masks, 0.05, 0.06, 0.8)
+    assignment = [[0, 3], [1, 2, 5], [4]]
+    total = torch.zeros(1, 2, 4, h, w, device="cuda")
+    for rows in assignment:
+        acc = torch.empty(1, 2, 4, h, w, device="cuda")
+        o.blend_partial(eps[:, rows].contiguous().cuda(), masks.cuda(), rows, acc)
+        total += acc                                   # stands in for the all-reduce
+    x0 = torch.empty_like(x).cuda()
+    got = o.blend_finish(x.cuda(), total, masks.cuda(), 0.05, 0.06, 0.8, x0_out=x0).cpu()
+    torch.testing.assert_close(x0.cpu(), want0, rtol=3e-5, atol=3e-4)
+    torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-4)
+
+
+def test_blend_in_place_and_errors():
+    o = ops()
+    x, eps = _blend_inputs(3, 16, 16, torch.bfloat16, 15)
+    masks = synth.fixture_masks(16, 16)
+    want, _ = sm.fused_step(x, eps[0].float(), masks, 0.3, 0.4, 0.8)
+    xc = x.cuda()
+    o.tweedie_blend_ddim(xc, eps.cuda(), masks.cuda(), 0.3, 0.4, 0.8, out=xc)
+    torch.testing.assert_close(xc.cpu(), want, rtol=2e-5, atol=2e-5)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        o.tweedie_blend_ddim(torch.zeros(1, 4, 3, 3).cuda(), torch.zeros(4, 4, 3, 3).cuda(), None, 0.3, 0.4, 0.8)
+    with pytest.raises(RuntimeError, match="alphas"):
+        o.tweedie_blend_ddim(xc, eps.cuda(), masks.cuda(), 0.0, 0.4, 0.8)
+
+
+GN_SHAPES = [  # (N, C, H, W) — SDXL sites at reduced spatial size plus ragged / tiny cases
+    (4, 320, 32, 32), (2, 640, 16, 16), (4, 1280, 8, 8), (2, 960, 16, 24), (1, 1920, 8, 8),
+    (2, 2560, 8, 8), (3, 64, 5, 7), (1, 32, 1, 8), (2, 320, 128, 128),
+]
+
+
+def _gn_ref(x, gamma, beta, groups, eps, add, silu):
+    xf = x.float()
+    if add is not None:
+        xf = xf + add[:, :, None, None]
+    y = F.group_norm(xf, groups, gamma, beta, eps)
+    return F.silu(y) if silu else y
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("layout", ["nhwc", "nchw"])
+@pytest.mark.parametrize("shape", GN_SHAPES)
+def test_groupnorm_matches_fp32_reference(dtype, layout, shape):
+    o = ops()
+    N, C, H, W = shape
+    if layout == "nchw" and (H * W) % 8:
+        pytest.skip("NCHW kernel requires HW % 8 == 0 (checked in test_groupnorm_errors)")
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(shape, generator=g) * 1.7 + 0.6 * torch.randn(1, C, 1, 1, generator=g)).to(dtype)
+    gamma, beta = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    add = 0.5 * torch.randn(N, C, generator=g)
+    for silu, use_add, eps in [(True, False, 1e-5), (False, False, 1e-6), (True, True, 1e-5)]:
+        want = _gn_ref(x, gamma, beta, 32, eps, add if use_add else None, silu)
+        xc = x.cuda()
+        if layout == "nhwc":
+            xc = xc.contiguous(memory_format=torch.channels_last)
+        got = o.group_norm(xc, gamma.cuda(), beta.cuda(), 32, eps, silu=silu, add=add.cuda() if use_add else None)
+        assert got.stride() == xc.stride()
+        if dtype == torch.float32:
+            torch.testing.assert_close(got.cpu(), want, rtol=3e-5, atol=3e-5)
+        else:
+            # one rounding of the output dtype (+ fp32 round-off before it)
+            torch.testing.assert_close(got.cpu().float(), want.to(dtype).float(),
+                                       rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
+
+
+def test_groupnorm_large_mean_is_stable_and_inplace():
+    """|mean| >> std: the pivot-shifted sums must not cancel catastrophically."""
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 320, 16, 16, generator=g) * 0.01 + 100.0
+    gamma, beta = torch.ones(320), torch.zeros(320)
+    want = _gn_ref(x, gamma, beta, 32, 1e-5, None, False)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    o.group_norm(xc, gamma.cuda(), beta.cuda(), 32, 1e-5, out=xc)
+    torch.testing.assert_close(xc.cpu(), want, rtol=2e-3, atol=2e-3)
+
+
+def test_groupnorm_errors():
+    o = ops()
+    with pytest.raises(RuntimeError, match="HW=35"):
+        o.group_norm(torch.zeros(1, 64, 5, 7).cuda(), torch.ones(64).cuda(), torch.zeros(64).cuda(), 32, 1e-5)
+    with pytest.raises(RuntimeError, match="not divisible"):
+        o.group_norm(torch.zeros(1, 40, 8, 8).cuda(), torch.ones(40).cuda(), torch.zeros(40).cuda(), 32, 1e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_residual_add(dtype):
+    o = ops()
+    g = torch.Generator().manual_seed(8)
+    for n in [(4, 320, 32, 32), (1, 8), (3, 1280, 24)]:
+        a, b = torch.randn(n, generator=g).to(dtype), torch.randn(n, generator=g).to(dtype)
+        for inv in (1.0, 0.5):
+            want = ((a.float() + b.float()) * inv).to(dtype)
+            got = o.residual_add(a.cuda(), b.cuda(), inv).cpu()
+            assert torch.equal(got, want)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        o.residual_add(torch.zeros(7).cuda(), torch.zeros(7).cuda())

@@ -1,0 +1,328 @@
+// k4 / k5 — GroupNorm (+ per-(n,c) additive bias before the norm, + SiLU), NHWC and NCHW.
+//
+// HBM-bound.  Two launches: `stats` reads x once (128-bit coalesced loads, 4 rows in flight per
+// thread) and writes per-CTA shifted partial sums; `apply` re-reads x — from the 126 MB L2 for
+// every SDXL activation that fits — folds the statistics, gamma, beta and the additive bias into
+// one fma per element, applies SiLU and stores once.  Statistics are fp32 sums of (x - pivot)
+// with a per-(n,group) pivot taken from the data, so E[d^2] - E[d]^2 has no catastrophic
+// cancellation; partials are combined in a fixed order (deterministic, no atomics).
+//
+// Replaces [D] diffusers ResnetBlock2D norm1/norm2 + SiLU (mirrored in the reference at
+// video_gen/utils_attn.py:391-431), conv_norm_out + SiLU, and Transformer2DModel.norm (no act).
+#include "tmx_common.cuh"
+
+namespace tmx {
+
+constexpr int kGnMaxParts = 1024;     // upper bound on partials per (n, group)
+constexpr int kGnMaxThreads = 512;
+
+template <typename T> struct V8 {
+    static constexpr int kBytes = 16;
+    static __device__ __forceinline__ void load(const T* p, float (&f)[8], bool keep) {
+        unpack8<T>(keep ? ld_keep(p) : ld_stream(p), f);
+    }
+    static __device__ __forceinline__ void store(T* p, const float (&f)[8]) { st_stream(p, pack8<T>(f)); }
+};
+template <> struct V8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&f)[8], bool) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+        st_stream(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+        st_stream(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+    }
+};
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float silu(float y) { return __fdividef(y, 1.f + __expf(-y)); }
+
+// ------------------------------------------------------------------------------------------ NHWC
+// grid (P, N); block = CV * RY threads (CV = C/8 channel vectors, RY row lanes).
+// Thread (ty, tx) owns channel vector tx and rows r = row0 + ty, + RY, ...
+template <typename T>
+__global__ void __launch_bounds__(kGnMaxThreads)
+gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __restrict__ part,
+              float* __restrict__ pivots, int C, int HW, int G, int rows_per_cta) {
+    extern __shared__ float2 sh[];                      // [RY][C]
+    const int CV = C >> 3, RY = blockDim.x / CV, cpg = C / G;
+    const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+    const int n = blockIdx.y, P = gridDim.x;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(HW, row0 + rows_per_cta);
+    const T* xn = x + (size_t)n * HW * C;
+
+    float piv[8], ad[8], S[8], SS[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = tx * 8 + j, g = c / cpg;
+        const float a0 = add ? add[(size_t)n * C + g * cpg] : 0.f;
+        piv[j] = to_f32<T>(xn[g * cpg]) + a0;           // pivot = x'[n, pixel 0, first channel of group]
+        ad[j] = add ? add[(size_t)n * C + c] : 0.f;
+        S[j] = 0.f; SS[j] = 0.f;
+    }
+    const T* col = xn + (size_t)tx * 8;
+    int r = row0 + ty;
+    for (; r + 3 * RY < row1; r += 4 * RY) {            // 4 independent 128-bit loads in flight
+        float f0[8], f1[8], f2[8], f3[8];
+        V8<T>::load(col + (size_t)r * C, f0, true);
+        V8<T>::load(col + (size_t)(r + RY) * C, f1, true);
+        V8<T>::load(col + (size_t)(r + 2 * RY) * C, f2, true);
+        V8<T>::load(col + (size_t)(r + 3 * RY) * C, f3, true);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float k = piv[j] - ad[j];
+            float d0 = f0[j] - k, d1 = f1[j] - k, d2 = f2[j] - k, d3 = f3[j] - k;
+            S[j] += (d0 + d1) + (d2 + d3);
+            SS[j] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, SS[j]))));
+        }
+    }
+    for (; r < row1; r += RY) {
+        float f0[8];
+        V8<T>::load(col + (size_t)r * C, f0, true);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d0 = f0[j] - (piv[j] - ad[j]);
+            S[j] += d0; SS[j] = fmaf(d0, d0, SS[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[(size_t)ty * C + tx * 8 + j] = make_float2(S[j], SS[j]);
+    __syncthreads();
+    // one warp per group, fixed summation order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < G; g += nwarps) {
+        float s = 0.f, ss = 0.f;
+        for (int i = lane; i < RY * cpg; i += 32) {
+            const float2 v = sh[(size_t)(i / cpg) * C + g * cpg + (i % cpg)];
+            s += v.x; ss += v.y;
+        }
+        s = warp_sum(s); ss = warp_sum(ss);
+        if (lane == 0) {
+            part[((size_t)n * G + g) * P + blockIdx.x] = make_float2(s, ss);
+            // the pivot is published once so that `apply` never re-reads x[0] (y may alias x)
+            if (blockIdx.x == 0)
+                pivots[n * G + g] = to_f32<T>(xn[g * cpg]) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGnMaxThreads)
+gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ add, const float2* __restrict__ part,
+              const float* __restrict__ pivots, T* __restrict__ y,
+              int C, int HW, int G, int rows_per_cta, int P_stats, float eps, int act) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int CV = C >> 3, RY = blockDim.x / CV, cpg = C / G;
+    const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+    const int n = blockIdx.y;
+    const T* xn = x + (size_t)n * HW * C;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float s = 0.f, ss = 0.f;
+        const float2* pp = part + ((size_t)n * G + g) * P_stats;
+        for (int i = 0; i < P_stats; ++i) { s += pp[i].x; ss += pp[i].y; }
+        const float inv = 1.f / ((float)HW * (float)cpg);
+        const float md = s * inv;
+        const float var = fmaxf(ss * inv - md * md, 0.f);
+        s_mean[g] = pivots[n * G + g] + md;
+        s_rstd[g] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = tx * 8 + j, g = c / cpg;
+        a[j] = s_rstd[g] * gamma[c];
+        const float adj = add ? add[(size_t)n * C + c] : 0.f;
+        b[j] = fmaf(adj - s_mean[g], a[j], beta[c]);
+    }
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
+    const T* col = xn + (size_t)tx * 8;
+    T* ycol = y + (size_t)n * HW * C + (size_t)tx * 8;
+    int r = row0 + ty;
+    for (; r + 3 * RY < row1; r += 4 * RY) {
+        float f[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) V8<T>::load(col + (size_t)(r + u * RY) * C, f[u], false);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = fmaf(f[u][j], a[j], b[j]);
+                f[u][j] = act ? silu(v) : v;
+            }
+            V8<T>::store(ycol + (size_t)(r + u * RY) * C, f[u]);
+        }
+    }
+    for (; r < row1; r += RY) {
+        float f[8];
+        V8<T>::load(col + (size_t)r * C, f, false);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = fmaf(f[j], a[j], b[j]);
+            f[j] = act ? silu(v) : v;
+        }
+        V8<T>::store(ycol + (size_t)r * C, f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ NCHW
+// (n, g) slab = cpg * HW contiguous elements.  grid (S, N*G), 256 threads, vectors of 8.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_stats_nchw(const T* __restrict__ x, const float* __restrict__ add, float2* __restrict__ part,
+              float* __restrict__ pivots, int C, int HW, int G, int vec_per_cta) {
+    __shared__ float2 red[8];
+    const int cpg = C / G, ng = blockIdx.y, n = ng / G, g = ng % G, S = gridDim.x;
+    const T* slab = x + ((size_t)n * C + (size_t)g * cpg) * HW;
+    const float* addn = add ? add + (size_t)n * C + g * cpg : nullptr;
+    const float piv = to_f32<T>(slab[0]) + (addn ? addn[0] : 0.f);
+    const int nvec = (cpg * HW) >> 3;
+    const int v0 = blockIdx.x * vec_per_cta, v1 = min(nvec, v0 + vec_per_cta);
+    float s = 0.f, ss = 0.f;
+    for (int v = v0 + threadIdx.x; v < v1; v += 256) {
+        float f[8];
+        V8<T>::load(slab + (size_t)v * 8, f, true);
+        const float k = piv - (addn ? addn[(v * 8) / HW] : 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = f[j] - k; s += d; ss = fmaf(d, d, ss); }
+    }
+    s = warp_sum(s); ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(s, ss);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 8; ++w) { a += red[w].x; b += red[w].y; }
+        part[(size_t)ng * S + blockIdx.x] = make_float2(a, b);
+        if (blockIdx.x == 0) pivots[ng] = piv;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_apply_nchw(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ add, const float2* __restrict__ part,
+              const float* __restrict__ pivots, T* __restrict__ y,
+              int C, int HW, int G, int vec_per_cta, int S_stats, float eps, int act) {
+    __shared__ float s_mr[2];
+    const int cpg = C / G, ng = blockIdx.y, n = ng / G, g = ng % G;
+    const T* slab = x + ((size_t)n * C + (size_t)g * cpg) * HW;
+    T* yslab = y + ((size_t)n * C + (size_t)g * cpg) * HW;
+    const float* addn = add ? add + (size_t)n * C + g * cpg : nullptr;
+    if (threadIdx.x == 0) {
+        float s = 0.f, ss = 0.f;
+        for (int i = 0; i < S_stats; ++i) { const float2 v = part[(size_t)ng * S_stats + i]; s += v.x; ss += v.y; }
+        const float inv = 1.f / ((float)HW * (float)cpg);
+        const float md = s * inv;
+        s_mr[0] = pivots[ng] + md;
+        s_mr[1] = rsqrtf(fmaxf(ss * inv - md * md, 0.f) + eps);
+    }
+    __syncthreads();
+    const float mean = s_mr[0], rstd = s_mr[1];
+    const int nvec = (cpg * HW) >> 3;
+    const int v0 = blockIdx.x * vec_per_cta, v1 = min(nvec, v0 + vec_per_cta);
+    for (int v = v0 + threadIdx.x; v < v1; v += 256) {
+        const int cl = (v * 8) / HW, c = g * cpg + cl;
+        const float a = rstd * gamma[c];
+        const float b = fmaf((addn ? addn[cl] : 0.f) - mean, a, beta[c]);
+        float f[8];
+        V8<T>::load(slab + (size_t)v * 8, f, false);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float t = fmaf(f[j], a, b); f[j] = act ? silu(t) : t; }
+        V8<T>::store(yslab + (size_t)v * 8, f);
+    }
+}
+
+struct GnPlan { int threads, RY, rows_per_cta, P; };
+
+static GnPlan plan_nhwc(int N, int C, int HW) {
+    GnPlan p;
+    const int CV = C / 8;
+    p.RY = kGnMaxThreads / CV;
+    if (p.RY > HW) p.RY = HW;
+    p.threads = CV * p.RY;
+    int want = (4 * sm_count() + N - 1) / N;                 // ~4 CTAs per SM over the whole grid
+    int rows = (HW + want - 1) / want;
+    const int min_rows = 8 * p.RY;                           // >= 8 rows per thread when possible
+    if (rows < min_rows) rows = min_rows;
+    rows = ((rows + p.RY - 1) / p.RY) * p.RY;
+    if (rows > HW) rows = HW;
+    p.rows_per_cta = rows;
+    p.P = (HW + rows - 1) / rows;
+    if (p.P > kGnMaxParts) { p.rows_per_cta = (HW + kGnMaxParts - 1) / kGnMaxParts; p.P = (HW + p.rows_per_cta - 1) / p.rows_per_cta; }
+    return p;
+}
+
+template <typename T>
+static int run_gn(const void* x, const float* gamma, const float* beta, const float* add, void* y, void* ws,
+                  int N, int C, int HW, int G, float eps, int act, int layout, cudaStream_t st) {
+    float* pivots = (float*)ws;                                // [N*G], padded to 16 B
+    float2* part = (float2*)((char*)ws + (((size_t)N * G * sizeof(float) + 15) & ~(size_t)15));
+    if (layout == TMX_NHWC) {
+        GnPlan p = plan_nhwc(N, C, HW);
+        dim3 grid(p.P, N);
+        size_t smem = (size_t)p.RY * C * sizeof(float2);
+        gn_stats_nhwc<T><<<grid, p.threads, smem, st>>>((const T*)x, add, part, pivots, C, HW, G, p.rows_per_cta);
+        TMX_CUDA(cudaGetLastError());
+        gn_apply_nhwc<T><<<grid, p.threads, 0, st>>>((const T*)x, gamma, beta, add, part, pivots, (T*)y, C, HW, G,
+                                                    p.rows_per_cta, p.P, eps, act);
+        return check_cuda(cudaGetLastError(), "gn_apply_nhwc launch");
+    }
+    const int cpg = C / G, nvec = cpg * HW / 8;
+    int S = (4 * sm_count() + N * G - 1) / (N * G);
+    int vec_per = (nvec + S - 1) / S;
+    if (vec_per < 1024) vec_per = 1024;                       // >= 4 vectors per thread
+    S = (nvec + vec_per - 1) / vec_per;
+    dim3 grid(S, N * G);
+    gn_stats_nchw<T><<<grid, 256, 0, st>>>((const T*)x, add, part, pivots, C, HW, G, vec_per);
+    TMX_CUDA(cudaGetLastError());
+    gn_apply_nchw<T><<<grid, 256, 0, st>>>((const T*)x, gamma, beta, add, part, pivots, (T*)y, C, HW, G, vec_per, S, eps, act);
+    return check_cuda(cudaGetLastError(), "gn_apply_nchw launch");
+}
+
+int groupnorm_init() {
+    // stats kernel may need up to RY*C*8 bytes = 512*8*8 = 32 KB dynamic smem: below the 48 KB default.
+    return TMX_OK;
+}
+
+}  // namespace tmx
+
+using namespace tmx;
+
+extern "C" size_t tmx_groupnorm_workspace_bytes(int N, int C, int HW, int G, int layout) {
+    (void)C; (void)HW; (void)layout;
+    if (N <= 0 || G <= 0) return 0;
+    return (((size_t)N * G * sizeof(float) + 15) & ~(size_t)15) + (size_t)N * G * kGnMaxParts * sizeof(float2);
+}
+
+extern "C" int tmx_groupnorm_fwd(const void* x, const float* gamma, const float* beta, const float* add,
+                                 void* y, void* workspace, int N, int C, int HW, int G, float eps,
+                                 int act, int layout, int dtype, void* stream) {
+    TMX_REQUIRE(x && gamma && beta && y && workspace, TMX_EINVAL, "groupnorm: null pointer");
+    TMX_REQUIRE(N > 0 && C > 0 && HW > 0 && G > 0, TMX_EINVAL, "groupnorm: non-positive size");
+    TMX_REQUIRE(G <= 64 && C % G == 0, TMX_ESHAPE, "groupnorm: C=%d not divisible by G=%d (G<=64)", C, G);
+    TMX_REQUIRE(act == TMX_ACT_NONE || act == TMX_ACT_SILU, TMX_EINVAL, "groupnorm: bad act %d", act);
+    TMX_REQUIRE(aligned16(x) && aligned16(y) && aligned16(workspace), TMX_EALIGN, "groupnorm: 16-byte alignment");
+    if (layout == TMX_NHWC) {
+        TMX_REQUIRE(C % 8 == 0 && C / 8 <= kGnMaxThreads, TMX_ESHAPE, "groupnorm NHWC: C=%d must be a multiple of 8 and <= %d", C, 8 * kGnMaxThreads);
+    } else if (layout == TMX_NCHW) {
+        TMX_REQUIRE(HW % 8 == 0, TMX_ESHAPE, "groupnorm NCHW: HW=%d must be a multiple of 8", HW);
+    } else {
+        set_error("groupnorm: bad layout %d", layout);
+        return TMX_EINVAL;
+    }
+    if (int rc = require_init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case TMX_F32:  return run_gn<float>(x, gamma, beta, add, y, workspace, N, C, HW, G, eps, act, layout, st);
+        case TMX_F16:  return run_gn<__half>(x, gamma, beta, add, y, workspace, N, C, HW, G, eps, act, layout, st);
+        case TMX_BF16: return run_gn<__nv_bfloat16>(x, gamma, beta, add, y, workspace, N, C, HW, G, eps, act, layout, st);
+    }
+    set_error("groupnorm: unsupported dtype %d", dtype);
+    return TMX_EDTYPE;
+}

@@ -1,0 +1,177 @@
+"""Torch-tensor front-ends of the libtmx C ABI (device pointers + sizes go straight through ctypes).
+
+PyTorch is plumbing here — it owns the device memory and the stream; all arithmetic of these ops
+is in the hand-written sm_100a kernels of ``csrc/``.  Nothing in this module falls back to a
+PyTorch implementation: non-CUDA tensors, unsupported shapes or a missing library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"tmx: unsupported dtype {t.dtype}") from None
+
+
+def _dev(*ts: torch.Tensor) -> int:
+    d = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("tmx ops run on CUDA tensors only (no CPU fallback)")
+        if d is None:
+            d = t.device.index
+        elif t.device.index != d:
+            raise RuntimeError("tmx: tensors on different devices")
+    _lib.init(d)
+    return d
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------ k7
+
+def tweedie_blend_ddim(x, eps, masks, a_t: float, a_next: float, g: float, *, is_last=False,
+                       weights=None, out=None, x0_out=None, ref_rounding=False):
+    """Fused CFG + Tweedie x0 + masked blend + DDIM (fusion_sampling.py:376-386,430,471-472).
+
+    x [imgs,C,H,W] fp32; eps [imgs*(K+1),C,H,W] or [imgs,K+1,C,H,W]; masks [K,1,H,W] fp32 or None.
+    Returns x_next (fp32, same shape as x)."""
+    _dev(x, eps, masks, out, x0_out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
+    imgs, Cc = x.shape[0], x.shape[1]
+    HW = x.shape[2] * x.shape[3]
+    rows = eps.numel() // (imgs * Cc * HW)
+    K = rows - 1
+    if masks is not None:
+        assert masks.dtype == torch.float32 and masks.is_contiguous() and masks.numel() == K * HW, "masks must be [K,1,H,W] fp32"
+    if out is None:
+        out = torch.empty_like(x)
+    w = None
+    if weights is not None:
+        assert len(weights) == K
+        w = (C.c_float * K)(*[float(v) for v in weights])
+    rc = _lib.load().tmx_tweedie_blend_ddim_fwd(
+        _p(x), _p(eps), _p(masks), w, _p(out), _p(x0_out), imgs, K, Cc, HW,
+        float(a_t), float(a_next), float(g), int(bool(is_last)), _dt(eps),
+        _lib.ROUND_REF if ref_rounding else _lib.ROUND_FP32, _stream())
+    _lib.check(rc, "tmx_tweedie_blend_ddim_fwd")
+    return out
+
+
+def blend_partial(eps_rows, masks, row_ids, acc, imgs: int = 1):
+    """acc[img,0] = sum m_c eps_c over owned concept rows; acc[img,1] = eps_u if owned else 0."""
+    _dev(eps_rows, masks, acc)
+    R = len(row_ids)
+    Cc, HW = eps_rows.shape[-3], eps_rows.shape[-2] * eps_rows.shape[-1]
+    K = masks.shape[0]
+    assert acc.dtype == torch.float32 and acc.numel() == imgs * 2 * Cc * HW and acc.is_contiguous()
+    assert eps_rows.is_contiguous() and eps_rows.numel() == imgs * R * Cc * HW
+    ids = (C.c_int * max(R, 1))(*[int(r) for r in row_ids])
+    rc = _lib.load().tmx_blend_partial_fwd(_p(eps_rows), _p(masks), ids, _p(acc), imgs, R, K, Cc, HW, _dt(eps_rows), _stream())
+    _lib.check(rc, "tmx_blend_partial_fwd")
+    return acc
+
+
+def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_out=None):
+    _dev(x, acc, masks, out, x0_out)
+    imgs, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    K = masks.shape[0]
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.load().tmx_blend_finish_fwd(_p(x), _p(acc), _p(masks), _p(out), _p(x0_out), imgs, K, Cc, HW,
+                                          float(a_t), float(a_next), float(g), int(bool(is_last)), _stream())
+    _lib.check(rc, "tmx_blend_finish_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ k4/k5
+
+_gn_ws = {}
+
+
+def _workspace(dev: int, nbytes: int) -> torch.Tensor:
+    ws = _gn_ws.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=f"cuda:{dev}")
+        _gn_ws[dev] = ws
+    return ws
+
+
+def group_norm(x, gamma, beta, groups: int, eps: float, *, silu=False, add=None, out=None):
+    """GroupNorm(+add[n,c] before the norm)(+SiLU).  ``x`` is a 4-D NCHW-shaped tensor that is either
+    contiguous (NCHW memory) or channels_last (NHWC memory); the output has the same memory format."""
+    d = _dev(x, gamma, beta, add, out)
+    N, Cc, H, W = x.shape
+    if x.is_contiguous():
+        layout = _lib.NCHW
+    elif x.is_contiguous(memory_format=torch.channels_last):
+        layout = _lib.NHWC
+    else:
+        raise RuntimeError("tmx.group_norm: x must be contiguous or channels_last")
+    if out is None:
+        out = torch.empty_like(x)          # preserves the memory format
+    assert out.stride() == x.stride() and out.dtype == x.dtype
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32, "gamma/beta must be fp32"
+    if add is not None:
+        assert add.dtype == torch.float32 and add.is_contiguous() and add.shape == (N, Cc)
+    lib = _lib.load()
+    ws = _workspace(d, lib.tmx_groupnorm_workspace_bytes(N, Cc, H * W, groups, layout))
+    rc = lib.tmx_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(add), _p(out), _p(ws), N, Cc, H * W, groups,
+                               float(eps), _lib.ACT_SILU if silu else _lib.ACT_NONE, layout, _dt(x), _stream())
+    _lib.check(rc, "tmx_groupnorm_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ k6
+
+def residual_add(a, b, inv_scale: float = 1.0, out=None):
+    """(a + b) * inv_scale; a and b must share dtype and memory layout (dense)."""
+    _dev(a, b, out)
+    assert a.dtype == b.dtype and a.shape == b.shape and a.stride() == b.stride()
+    if out is None:
+        out = torch.empty_like(a)
+    assert out.stride() == a.stride()
+    rc = _lib.load().tmx_resadd_fwd(_p(a), _p(b), _p(out), a.numel(), float(inv_scale), _dt(a), _stream())
+    _lib.check(rc, "tmx_resadd_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ k1/k2
+
+def attention(q, k, v, heads: int, scale: float | None = None, out=None):
+    """softmax(scale * q k^T) v per head, head_dim 64.  q [B,Nq,H*64], k/v [B,Nk,H*64] — the
+    diffusers layout *before* head_to_batch_dim (utils_custom.py:73-91); last dim contiguous,
+    token stride free (so q/k/v may be column slices of one fused projection)."""
+    _dev(q, k, v, out)
+    B, Nq, HD = q.shape
+    Nk = k.shape[1]
+    D = HD // heads
+    assert q.dtype == k.dtype == v.dtype and q.stride(2) == k.stride(2) == v.stride(2) == 1
+    for t, n in ((q, Nq), (k, Nk), (v, Nk)):
+        assert t.stride(0) == n * t.stride(1), "batch stride must equal N * token stride"
+    if out is None:
+        out = torch.empty((B, Nq, HD), dtype=q.dtype, device=q.device)
+    if scale is None:
+        scale = D ** -0.5
+    rc = _lib.load().tmx_attn_fwd(_p(q), _p(k), _p(v), _p(out), B, heads, Nq, Nk, D,
+                                  q.stride(1), k.stride(1), v.stride(1), out.stride(1),
+                                  float(scale), _dt(q), _stream())
+    _lib.check(rc, "tmx_attn_fwd")
+    return out
