@@ -149,6 +149,9 @@ TMX_API int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o,
                  int64_t q_stride_n, int64_t k_stride_n, int64_t v_stride_n, int64_t o_stride_n,
                  float scale, int dtype, void* stream);
 
+/* Tuning / test hook: force the number of 128-row query tiles per CTA (1 or 2); 0 = heuristic. */
+TMX_API int tmx_attn_set_variant(int nq);
+
 /* ---------------------------------------------------------------------------------------------
  * k3 — per-row routed projection (grouped GEMM over batch rows, one weight matrix per row):
  *   y[b] = x[b] @ W[b]^T (+ (x[b] @ down[b]^T) @ up[b]^T)          b = 0..B-1

@@ -1,0 +1,96 @@
+"""-m gpu: tcgen05 attention (k1/k2) through the C ABI vs the oracle's naive einsum-softmax-einsum
+(oracle/hooks_ref._sdpa_naive, the restatement of utils_custom.py:91-105) evaluated in fp32 on the
+same 16-bit inputs.
+
+Tolerance: P is rounded to the I/O dtype before the PV product and O is rounded once on store, so
+|err| <= ~2^-9 (bf16) / 2^-12 (fp16) relative to max|V| (~4.5 for randn) -> atol 2e-2 / 4e-3."""
+import pytest
+import torch
+
+from oracle.hooks_ref import _sdpa_naive
+
+pytestmark = pytest.mark.gpu
+
+ATOL = {torch.bfloat16: 2e-2, torch.float16: 4e-3}
+
+
+def ops():
+    from tweediemix_b200 import build, ops as o
+    build.build()
+    return o
+
+
+class _Heads:
+    def __init__(self, heads):
+        self.heads, self.scale = heads, 64 ** -0.5
+
+    def head_to_batch_dim(self, t):
+        b, n, c = t.shape
+        return t.reshape(b, n, self.heads, 64).permute(0, 2, 1, 3).reshape(b * self.heads, n, 64)
+
+    def batch_to_head_dim(self, t):
+        bh, n, d = t.shape
+        return t.reshape(bh // self.heads, self.heads, n, d).permute(0, 2, 1, 3).reshape(bh // self.heads, n, self.heads * d)
+
+
+def _ref(q, k, v, heads):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _sdpa_naive(_Heads(heads), q.float(), k.float(), v.float())
+
+
+SHAPES = [  # B, H, Nq, Nk
+    (1, 1, 128, 128), (2, 3, 256, 384), (1, 2, 200, 77), (1, 5, 130, 129), (1, 1, 1, 1), (3, 2, 77, 300),
+    (4, 10, 4096, 4096),      # SDXL 128x128 latents, K=3: the attn1 sites of down_blocks.1 / up_blocks.1
+    (4, 20, 1024, 1024),      # ... of down_blocks.2 / mid / up_blocks.0
+    (4, 10, 4096, 77), (4, 20, 1024, 77),   # attn2 (cross) sites
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("nq", [1, 2])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_attention_matches_oracle(shape, nq, dtype):
+    o = ops()
+    from tweediemix_b200 import _lib
+    B, H, Nq, Nk = shape
+    g = torch.Generator().manual_seed(Nq + 3 * Nk + H)
+    q = torch.randn(B, Nq, H * 64, generator=g).to(dtype).cuda()
+    k = torch.randn(B, Nk, H * 64, generator=g).to(dtype).cuda()
+    v = torch.randn(B, Nk, H * 64, generator=g).to(dtype).cuda()
+    _lib.load().tmx_attn_set_variant(nq)
+    try:
+        got = o.attention(q, k, v, H)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().tmx_attn_set_variant(0)
+    want = _ref(q, k, v, H)
+    err = (got.float() - want).abs().max().item()
+    assert torch.isfinite(got.float()).all()
+    assert err <= ATOL[dtype], f"max|diff| {err}"
+
+
+def test_attention_large_logits_and_strided_qkv():
+    """Peaked softmax (|logit| ~ 60: exercises the running-max / lazy-rescale path) and q/k/v given as
+    column slices of one fused [B, N, 3*H*64] projection output (token stride 3*H*64)."""
+    o = ops()
+    B, H, N = 2, 4, 640
+    g = torch.Generator().manual_seed(1)
+    qkv = torch.randn(B, N, 3 * H * 64, generator=g)
+    qkv[..., :2 * H * 64] *= 4.0
+    # make later kv tiles contain the largest logits so the reference max moves late
+    qkv[:, N // 2:, H * 64:2 * H * 64] *= 1.5
+    qkv = qkv.to(torch.bfloat16).cuda()
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    got = o.attention(q, k, v, H)
+    want = _ref(q, k, v, H)
+    assert (got.float() - want).abs().max().item() <= 3e-2
+
+
+def test_attention_errors():
+    o = ops()
+    z = torch.zeros(1, 8, 96, dtype=torch.bfloat16).cuda()
+    with pytest.raises(RuntimeError, match="head dim"):
+        o.attention(z, z, z, 2)                      # D = 48
+    z32 = torch.zeros(1, 8, 64).cuda()
+    with pytest.raises(RuntimeError, match="dtype"):
+        o.attention(z32, z32, z32, 1)

@@ -38,18 +38,30 @@ def _blend_inputs(K, h, w, dtype, seed, imgs=1):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("K,hw", [(3, (128, 128)), (3, (32, 32)), (8, (128, 128)), (1, (16, 8))])
 def test_blend_ref_rounding_matches_oracle(dtype, K, hw):
+    """TMX_ROUND_REF reproduces the reference's own mixed-precision arithmetic.  The reference runs
+    fusion_sampling.py:376-386,430 with CUDA tensors and 0-dim fp32 *CPU* alphas (App. B); the oracle
+    functions are device-agnostic restatements of those lines, so evaluating them on CUDA tensors here
+    IS the reference arithmetic as torch executes it on this GPU (fp16 products rounded once from an
+    fp32 scalar, division by a CPU scalar done as multiplication by its reciprocal).  Bit-exact up to
+    fma contraction: tolerance 2 fp32 ulp of the largest value.  Against the CPU evaluation of the same
+    oracle (which rounds the scalar to 16 bits first) the tolerance is one 16-bit ulp of eps amplified
+    by sqrt(1-a)/sqrt(a)."""
     o = ops()
     h, w = hw
     masks = synth.fixture_masks(h, w) if K == 3 else synth.stripe_masks(K, h, w)
     x, eps = _blend_inputs(K, h, w, dtype, 11)
+    ulp16 = {torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8, torch.float32: 2.0 ** -24}[dtype]
     for (at, an, last) in [(0.043827, 0.051787, False), (0.005844, 0.007365, False), (0.99915, 0.99915, True)]:
-        want, want0 = sm.fused_step(x, eps[0], masks, at, an, 0.8, is_last=last)
         x0 = torch.empty_like(x).cuda()
         got = o.tweedie_blend_ddim(x.cuda(), eps.cuda(), masks.cuda(), at, an, 0.8, is_last=last,
                                    x0_out=x0, ref_rounding=True).cpu()
-        scale = want.abs().max().item()
-        assert (got - want).abs().max().item() <= 4 * 1.2e-7 * max(scale, 1.0) * 8, (dtype, K, at)
-        torch.testing.assert_close(x0.cpu(), want0, rtol=2e-6, atol=2e-6 * max(scale, 1.0))
+        ref_dev, ref0_dev = sm.fused_step(x.cuda(), eps[0].cuda(), masks.cuda(), at, an, 0.8, is_last=last)
+        scale = max(ref_dev.abs().max().item(), 1.0)
+        assert (got - ref_dev.cpu()).abs().max().item() <= 2 * 1.2e-7 * scale, (dtype, K, at, "vs torch-CUDA reference arithmetic")
+        assert (x0.cpu() - ref0_dev.cpu()).abs().max().item() <= 2 * 1.2e-7 * max(ref0_dev.abs().max().item(), 1.0)
+        want, _ = sm.fused_step(x, eps[0], masks, at, an, 0.8, is_last=last)          # CPU evaluation
+        amp = ((1 - at) ** 0.5 / at ** 0.5) * eps.float().abs().max().item()
+        assert (got - want).abs().max().item() <= 4 * ulp16 * amp + 1e-5 * scale, (dtype, K, at, "vs CPU oracle")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "tmx_groupnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "tmx_resadd_fwd": (_i, [_vp, _vp, _vp, _sz, _f, _i, _vp]),
     "tmx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _f, _i, _vp]),
+    "tmx_attn_set_variant": (_i, [_i]),
     "tmx_routed_linear_fwd": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

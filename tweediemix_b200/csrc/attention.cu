@@ -1,8 +1,470 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// k1 / k2 — attention forward for head_dim 64 on sm_100a:  O = softmax(scale * Q K^T) V.
+//
+// Blackwell-native structure (no mma.sync / wgmma):
+//   * Q, K, V tiles are staged global -> shared by TMA (cp.async.bulk.tensor.4d, SWIZZLE_128B)
+//     straight from the [B, N, H, 64] tensors diffusers hands the hook, no permute;
+//   * S = Q K^T and O += P V are tcgen05.mma (kind::f16, M=128) issued by ONE elected thread,
+//     accumulators live in TMEM; P is written back to TMEM as packed 16-bit and consumed as the
+//     A operand of the second MMA (TS form), so P never touches shared memory;
+//   * warp-specialised: warp 0 = TMA producer (+ TMEM alloc), warp 1 = MMA issuer, then one
+//     128-thread softmax group per 128-row query tile (thread == row == TMEM lane), all linked by
+//     mbarriers; tcgen05.commit signals MMA completion;
+//   * online softmax in the exp2 domain with lazy rescaling of O (only when the running max
+//     moves by more than 2^8), exact because the row sum is accumulated against the same
+//     reference.
+// NQ = query tiles per CTA.  NQ=1: 192 threads, 256 TMEM columns, two CTAs per SM overlap each
+// other's softmax and MMA phases.  NQ=2: 320 threads, 512 TMEM columns, the two tiles ping-pong on
+// the tensor pipe and share every K/V tile (half the L2->SMEM traffic).
+//
+// Replaces the einsum -> softmax -> einsum of fusion_generation/utils_custom.py:91-105 and
+// utils_lora.py:99-113 (which materialise the [B*h, N, N] score tensor).
 #include "tmx_common.cuh"
-namespace tmx { int attn_init() { return TMX_OK; } }
-extern "C" int tmx_attn_fwd(const void*, const void*, const void*, void*, int, int, int, int, int,
-                            int64_t, int64_t, int64_t, int64_t, float, int, void*) {
-    tmx::set_error("tmx_attn_fwd: not built yet");
-    return TMX_ESHAPE;
+#include <cuda.h>
+
+namespace tmx {
+
+constexpr int kD = 64;               // head dim
+constexpr int kBM = 128;             // query rows per tile  (UMMA M)
+constexpr int kBN = 128;             // kv rows per tile     (UMMA N of QK^T, K of PV)
+constexpr int kTileBytes = kBM * kD * 2;         // 16 KiB, one 128x64 16-bit tile
+constexpr float kRescaleThreshold = 8.0f;        // log2 domain
+
+__device__ unsigned int g_attn_timeout_flag = 0;
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must end in a trap (CUDA error), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {            // ~2 s
+            atomicExch(&g_attn_timeout_flag, 1u);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
+           "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+#define TMX_R8(r, o)  "=r"(r[o+0]), "=r"(r[o+1]), "=r"(r[o+2]), "=r"(r[o+3]), "=r"(r[o+4]), "=r"(r[o+5]), "=r"(r[o+6]), "=r"(r[o+7])
+#define TMX_I8(r, o)  "r"(r[o+0]), "r"(r[o+1]), "r"(r[o+2]), "r"(r[o+3]), "r"(r[o+4]), "r"(r[o+5]), "r"(r[o+6]), "r"(r[o+7])
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : TMX_R8(r, 0), TMX_R8(r, 8), TMX_R8(r, 16), TMX_R8(r, 24) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :: "r"(taddr), TMX_I8(r, 0), TMX_I8(r, 8), TMX_I8(r, 16), TMX_I8(r, 24) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :: "r"(taddr), TMX_I8(r, 0), TMX_I8(r, 8) : "memory");
+}
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ------------------------------------------------------------------------- UMMA descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) |
+// SBO>>4 [32,46) | version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16, int M, int N, bool b_mn_major) {
+    return (1u << 4)                              // c_format = F32
+         | ((bf16 ? 1u : 0u) << 7)                // a_format
+         | ((bf16 ? 1u : 0u) << 10)               // b_format
+         | (0u << 15)                             // a_major = K
+         | ((b_mn_major ? 1u : 0u) << 16)         // b_major
+         | ((uint32_t)(N >> 3) << 17)             // n_dim
+         | ((uint32_t)(M >> 4) << 24);            // m_dim
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if constexpr (BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+// ------------------------------------------------------------------------------------- kernel
+template <int NQ> struct AttnCfg {
+    static constexpr int kStages = NQ == 1 ? 2 : 3;
+    static constexpr int kThreads = 64 + 128 * NQ;
+    static constexpr int kTmemCols = 256 * NQ;                     // per tile: S[0,128) O[128,192) P[192,256)
+    static constexpr int kBars = 3 * NQ + NQ + 4 * kStages;        // s_full,p_full,o_full,q_full + k/v full/empty
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + (NQ + 2 * kStages) * kTileBytes + kBars * 8 + 16;
+};
+
+template <int NQ, bool BF16>
+__global__ void __launch_bounds__(AttnCfg<NQ>::kThreads, NQ == 1 ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, void* __restrict__ o_ptr, long long o_stride_n,
+                int Nq, int Nk, int H, float scale_log2) {
+    using Cfg = AttnCfg<NQ>;
+    constexpr int ST = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + NQ * kTileBytes;
+    uint8_t* sV = sK + ST * kTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * kTileBytes);
+    uint64_t* q_full = bars;                   // [NQ]
+    uint64_t* s_full = q_full + NQ;            // [NQ]
+    uint64_t* p_full = s_full + NQ;            // [NQ]
+    uint64_t* o_full = p_full + NQ;            // [NQ]
+    uint64_t* k_full = o_full + NQ;            // [ST]
+    uint64_t* k_empty = k_full + ST;
+    uint64_t* v_full = k_empty + ST;
+    uint64_t* v_empty = v_full + ST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + ST);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (kBM * NQ), h = blockIdx.y, b = blockIdx.z;
+    const int T = (Nk + kBN - 1) / kBN;
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+        for (int i = 0; i < ST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        if (lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
+        __syncwarp();
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            for (int w = 0; w < NQ; ++w) {
+                mbar_expect_tx(&q_full[w], kTileBytes);
+                tma_load_4d(sQ + w * kTileBytes, &tm_q, &q_full[w], 0, h, q0 + w * kBM, b);
+            }
+            for (int j = 0; j < T; ++j) {
+                const int st = j % ST;
+                const uint32_t ph = (uint32_t)(j / ST) & 1u;
+                mbar_wait(&k_empty[st], ph ^ 1u);
+                mbar_expect_tx(&k_full[st], kTileBytes);
+                tma_load_4d(sK + st * kTileBytes, &tm_k, &k_full[st], 0, h, j * kBN, b);
+                mbar_wait(&v_empty[st], ph ^ 1u);
+                mbar_expect_tx(&v_full[st], kTileBytes);
+                tma_load_4d(sV + st * kTileBytes, &tm_v, &v_full[st], 0, h, j * kBN, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = make_idesc(BF16, kBM, kBN, false);
+            constexpr uint32_t idesc_pv = make_idesc(BF16, kBM, kD, true);
+            auto issue_qk = [&](int w, int st) {
+                const uint32_t a0 = smem_u32(sQ + w * kTileBytes), b0 = smem_u32(sK + st * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kD / 16; ++k)                    // 4 x (K = 16): +32 B inside the 128 B swizzle row
+                    umma_ss(tmem_base + w * 256, make_sw128_desc(a0 + k * 32, 16, 1024),
+                            make_sw128_desc(b0 + k * 32, 16, 1024), idesc_qk, k > 0);
+            };
+            auto issue_pv = [&](int w, int st, bool acc) {
+                const uint32_t b0 = smem_u32(sV + st * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBN / 16; ++k)                   // 8 x (K = 16 kv rows): +2048 B in V, +8 columns in P
+                    umma_ts(tmem_base + w * 256 + 128, tmem_base + w * 256 + 192 + k * 8,
+                            make_sw128_desc(b0 + k * 2048, 16, 1024), idesc_pv, (acc || k > 0) ? 1u : 0u);
+            };
+            mbar_wait(&k_full[0], 0);
+            for (int w = 0; w < NQ; ++w) {
+                mbar_wait(&q_full[w], 0);
+                tc_fence_after();
+                issue_qk(w, 0);
+                umma_commit(&s_full[w]);
+            }
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < T; ++j) {
+                const int st = j % ST, stn = (j + 1) % ST;
+                const uint32_t ph = (uint32_t)(j / ST) & 1u, phn = (uint32_t)((j + 1) / ST) & 1u;
+                for (int w = 0; w < NQ; ++w) {
+                    mbar_wait(&p_full[w], (uint32_t)j & 1u);
+                    if (w == 0) mbar_wait(&v_full[st], ph);
+                    tc_fence_after();
+                    issue_pv(w, st, j > 0);
+                    if (w == NQ - 1) umma_commit(&v_empty[st]);
+                    if (j + 1 < T) {
+                        if (w == 0) { mbar_wait(&k_full[stn], phn); tc_fence_after(); }
+                        issue_qk(w, stn);
+                        umma_commit(&s_full[w]);
+                        if (w == NQ - 1) umma_commit(&k_empty[stn]);
+                    } else {
+                        umma_commit(&o_full[w]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================ softmax / correction / epilogue ==============
+        const int w = (warp - 2) >> 2;                       // query tile handled by this warp group
+        const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;                 // row in the tile == TMEM lane
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + w * 256;
+        float m_ref = -INFINITY;                             // running reference max, log2 domain (scaled)
+        float l_sum = 0.f;
+
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&s_full[w], (uint32_t)j & 1u);
+            tc_fence_after();
+            uint32_t s[128];
+            tmem_ld32(t_row + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+            tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+            tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+            tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+            tc_wait_ld();
+            const int valid = Nk - j * kBN;
+            if (valid < kBN) {
+#pragma unroll
+                for (int c = 0; c < 128; ++c) if (c >= valid) s[c] = 0xff800000u;   // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 128; c += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(s[c])); mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(s[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+            }
+            const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+            // lazy rescale: move the reference only when the max grew by more than 2^8
+            const bool bump = m_tile > m_ref + kRescaleThreshold;
+            const float m_new = bump ? m_tile : m_ref;
+            if (j > 0 && __any_sync(0xffffffffu, bump)) {            // warp-uniform: tcgen05.ld/st are warp-collective
+                const float alpha = bump ? ex2(m_ref - m_new) : 1.f;
+                l_sum *= alpha;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t o[32];
+                    tmem_ld32(t_row + 128 + half * 32, o);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                    tmem_st32(t_row + 128 + half * 32, o);
+                }
+            }
+            m_ref = m_new;
+            float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t p[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float e0 = ex2(fmaf(__uint_as_float(s[q * 32 + 2 * c]), scale_log2, -m_new));
+                    const float e1 = ex2(fmaf(__uint_as_float(s[q * 32 + 2 * c + 1]), scale_log2, -m_new));
+                    sum0 += e0; sum1 += e1;
+                    p[c] = pack2<BF16>(e0, e1);
+                }
+                tmem_st16(t_row + 192 + q * 16, p);
+            }
+            l_sum += sum0 + sum1;
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_full[w]);
+        }
+
+        // epilogue: O / l -> global (row-contiguous 128 B per thread)
+        mbar_wait(&o_full[w], 0);
+        tc_fence_after();
+        const float inv_l = 1.f / l_sum;
+        const int q_row = q0 + w * kBM + row;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(o_ptr) +
+                       (((size_t)b * Nq + (size_t)q_row) * (size_t)o_stride_n + (size_t)h * kD) * 2;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t o[32];
+            tmem_ld32(t_row + 128 + half * 32, o);
+            tc_wait_ld();
+            if (q_row < Nq) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 v;
+                    v.x = pack2<BF16>(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+                    v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+                    v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+                    v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(dst + (half * 32 + c) * 2) = v;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int attn_init() {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TMX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        TMX_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, TMX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+        g_encode = (EncodeTiledFn)fn;
+    }
+    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1>::kSmemBytes));
+    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1>::kSmemBytes));
+    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<2>::kSmemBytes));
+    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<2>::kSmemBytes));
+    return TMX_OK;
+}
+
+// [B, N, H, 64] 16-bit tensor with token stride `stride_n` elements -> 4-D map (d, h, n, b), box 64 x 1 x 128 x 1
+static int make_map(CUtensorMap* m, const void* base, int B, int N, int H, int64_t stride_n, bool bf16) {
+    cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)kD * 2, (cuuint64_t)stride_n * 2, (cuuint64_t)N * (cuuint64_t)stride_n * 2};
+    cuuint32_t box[4] = {kD, 1, kBM, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TMX_ECUDA; }
+    return TMX_OK;
+}
+
+static int g_force_nq = 0;   // test hook: 0 = heuristic
+
+}  // namespace tmx
+
+using namespace tmx;
+
+extern "C" int tmx_attn_set_variant(int nq) {
+    TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1 or 2");
+    g_force_nq = nq;
+    return TMX_OK;
+}
+
+extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o,
+                            int B, int H, int Nq, int Nk, int D,
+                            int64_t q_stride_n, int64_t k_stride_n, int64_t v_stride_n, int64_t o_stride_n,
+                            float scale, int dtype, void* stream) {
+    TMX_REQUIRE(q && k && v && o, TMX_EINVAL, "attn: null pointer");
+    TMX_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, TMX_EINVAL, "attn: non-positive size");
+    TMX_REQUIRE(D == kD, TMX_ESHAPE, "attn: head dim %d unsupported (only 64)", D);
+    TMX_REQUIRE(dtype == TMX_F16 || dtype == TMX_BF16, TMX_EDTYPE, "attn: dtype %d unsupported (fp16/bf16 only)", dtype);
+    TMX_REQUIRE(B <= 65535 && H <= 65535, TMX_ESHAPE, "attn: B or H too large for the grid");
+    const int64_t hd = (int64_t)H * kD;
+    TMX_REQUIRE(q_stride_n >= hd && k_stride_n >= hd && v_stride_n >= hd && o_stride_n >= hd, TMX_ESHAPE,
+                "attn: token stride smaller than H*64");
+    TMX_REQUIRE(q_stride_n % 8 == 0 && k_stride_n % 8 == 0 && v_stride_n % 8 == 0 && o_stride_n % 8 == 0, TMX_EALIGN,
+                "attn: token strides must be multiples of 8 elements");
+    TMX_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), TMX_EALIGN, "attn: 16-byte alignment");
+    if (int rc = require_init()) return rc;
+
+    const bool bf16 = dtype == TMX_BF16;
+    CUtensorMap mq, mk, mv;
+    if (int rc = make_map(&mq, q, B, Nq, H, q_stride_n, bf16)) return rc;
+    if (int rc = make_map(&mk, k, B, Nk, H, k_stride_n, bf16)) return rc;
+    if (int rc = make_map(&mv, v, B, Nk, H, v_stride_n, bf16)) return rc;
+    const float scale_log2 = scale * 1.4426950408889634f;
+    cudaStream_t st = (cudaStream_t)stream;
+    // two query tiles per CTA when there is enough work to fill the machine with them
+    int nq = g_force_nq ? g_force_nq : ((Nq > kBM && (long long)B * H * ((Nq + 255) / 256) >= sm_count()) ? 2 : 1);
+    if (nq == 2) {
+        dim3 grid((Nq + 2 * kBM - 1) / (2 * kBM), H, B);
+        if (bf16) attn_fwd_kernel<2, true><<<grid, AttnCfg<2>::kThreads, AttnCfg<2>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
+        else      attn_fwd_kernel<2, false><<<grid, AttnCfg<2>::kThreads, AttnCfg<2>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
+    } else {
+        dim3 grid((Nq + kBM - 1) / kBM, H, B);
+        if (bf16) attn_fwd_kernel<1, true><<<grid, AttnCfg<1>::kThreads, AttnCfg<1>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
+        else      attn_fwd_kernel<1, false><<<grid, AttnCfg<1>::kThreads, AttnCfg<1>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
+    }
+    return check_cuda(cudaGetLastError(), "attn_fwd_kernel launch");
 }

@@ -14,6 +14,7 @@ constexpr int kMaxConcepts = 16;
 struct BlendCoef {
     float s_t;        // sqrt(1 - a_t)
     float sqrt_at;    // sqrt(a_t)
+    float inv_sqrt_at;// 1 / sqrt(a_t), fp32 (what ATen's CUDA div-by-CPU-scalar multiplies with)
     float sqrt_an;    // sqrt(a_next)
     float s_n;        // sqrt(1 - a_next)
     float g;
@@ -80,7 +81,7 @@ blend_kernel(const float* __restrict__ x, const T* __restrict__ eps, const float
                     d = Pack2<T>::round(__fmul_rn(cf.g, d));
                     float e = Pack2<T>::round(__fadd_rn(eu[i], d));
                     float se = Pack2<T>::round(__fmul_rn(cf.s_t, e));
-                    t = __fdiv_rn(__fsub_rn(xv[i], se), cf.sqrt_at);
+                    t = __fmul_rn(__fsub_rn(xv[i], se), cf.inv_sqrt_at);
                     if (masks) t = __fmul_rn(m[i], t);
                     if (cf.has_w) t = __fmul_rn(w, t);
                     acc[i] = __fadd_rn(acc[i], t);
@@ -187,6 +188,7 @@ static BlendCoef make_coef(float a_t, float a_next, float g, int is_last, const 
     BlendCoef cf{};
     cf.s_t = sqrtf(1.0f - a_t);        // fp32 like the reference's 0-dim fp32 tensors (App. B)
     cf.sqrt_at = sqrtf(a_t);
+    cf.inv_sqrt_at = 1.0f / cf.sqrt_at;
     cf.sqrt_an = sqrtf(a_next);
     cf.s_n = sqrtf(1.0f - a_next);
     cf.g = g;
