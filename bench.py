@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the TweedieMix fusion-sampling hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): 1024px images/sec @ 50 DDIM steps, K concepts (+ per-denoise-step ms).
+One "step" of this benchmark = ONE COMPLETE IMAGE: the reference's 50-step schedule for
+BASELINE configs[1] (SDXL 1024x1024, K=2 foreground concepts + background => concept_num 3,
+U-Net batch 4, guidance 0.8, t_cond 0.2, 10 resampling iterations at step 0) = 242 U-Net
+sample-forwards + 71 fused CFG/Tweedie/blend/DDIM launches.  Region masks are precomputed inputs
+(north star), so the output-neutral jump loop / VAE / segmentation subprocess are not run.
+Weights, text embeddings and the start latent are seeded synthetic data (no network, no checkpoints).
+
+  value : images/s with all inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e   : same through the public API (Tweediemix.set_masks / set_text / sample_loop) starting from
+          pinned HOST buffers: per image the masks, text embeddings and start latent are copied H2D
+          (and the cross-attention K/V cache re-projected) and the final latent is read back D2H.
+  roofline     : the dominant hand-written kernel (tcgen05 attention), timed per launch with CUDA
+                 events in an instrumented eager pass of one fused denoise step, after the timed region.
+  cpu_baseline : oracle port of the reference's PyTorch CPU path on the host cores (rank 0, N=1).
+
+Multi-GPU (--gpus N): concept-parallel groups of G = min(N, K+1 = 4) ranks share one image (batch
+rows sharded, one all-reduce per step); N/G groups run different images concurrently.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_CONCEPTS = 3                      # concept_num incl. background (BASELINE "K=2 (cat+dog)" + background)
+FORWARDS_PER_IMAGE = 242
+MASK_DIR = os.path.join(ROOT, "tests", "golden", "masks", "test_out")
+MASK_NAMES = "a cat+a dog"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--variant", default="custom", choices=["custom", "lora"])
+    p.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    p.add_argument("--workload", default="image50", choices=["image50", "fused_step"],
+                   help="image50 = one full 50-step image per step (the metric); fused_step = one fused-phase denoise step (profiling)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graphs", action="store_true")
+    p.add_argument("--seed", type=int, default=3821)
+    p.add_argument("--ncu-range", action="store_true",
+                   help="profiling aid: after warm-up run ONE eager fused denoise step between cudaProfilerStart/Stop and exit "
+                        "(use with ncu --profile-from-start off)")
+    return p.parse_args()
+
+
+def namespace(variant):
+    return argparse.Namespace(guidance_scale=0.8, n_timesteps=50, t_cond=0.2, t_stop=0.8 if variant == "lora" else None,
+                              resampling_steps=10, jumping_steps=5, resolution_h=1024, resolution_w=1024,
+                              crops_coords_top_left_h=0, crops_coords_top_left_w=0, seed=3821, output_path=".",
+                              seg_concepts=MASK_NAMES, seg_gpu=0)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = max(smax, float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ================================================================================ reference arm (CPU)
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.cpu_baseline import CpuReference
+    ref = CpuReference(res=1024)
+    for _ in range(min(args.warmup, 1)):            # one warm-up forward is enough on CPU (allocator, thread pool)
+        ref.forward_seconds()
+    t = [ref.forward_seconds() for _ in range(args.steps)]
+    sec = sum(t) / len(t)
+    val = CpuReference.images_per_second(sec)
+    line = {"impl": "reference", "metric": "1024px images/sec @50 DDIM steps, K concepts", "value": val, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / val,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1, 1), "gpu_launches": 0,
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": ref.threads, "kind": "port", "sample": ref.sample_description(),
+                             "seconds_per_sample_forward": sec},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, group, n_groups):
+    return {"workload": "SDXL-base U-Net 1024x1024 (latent 128x128), K=2 concepts + background (concept_num 3, U-Net batch 4), "
+                        "50 DDIM steps, guidance 0.8, t_cond 0.2, 10 resampling iterations; masks precomputed",
+            "baseline_config": "configs[1]", "variant": args.variant, "step_unit": "one 50-step image" if args.workload == "image50" else "one fused denoise step",
+            "sample_forwards_per_image": FORWARDS_PER_IMAGE, "parallelism": f"concept-parallel x{group}, {n_groups} image group(s)",
+            "cuda_graphs": not args.no_graphs,
+            "l2": "no flush needed: every step streams 5.1 GB of bf16 weights (>> 126 MB L2)"}
+
+
+# ================================================================================ our arm (GPU)
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from tweediemix_b200 import build, ops
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    from tweediemix_b200.fusion_sampling import Tweediemix
+    from tweediemix_b200.masks import load_region_masks
+    from tweediemix_b200.synthetic import make_components, make_text
+    from tweediemix_b200.unet import UNetConfig
+
+    group_size = min(world, K_CONCEPTS + 1)
+    n_groups = max(world // group_size, 1)
+    my_group = rank // group_size
+    pg = None
+    if world > 1:
+        for gi in range(n_groups):                    # every rank must create every group
+            g = dist.new_group(list(range(gi * group_size, (gi + 1) * group_size)))
+            if gi == my_group:
+                pg = g
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    masks_host = load_region_masks(MASK_DIR, MASK_NAMES, 128, 128).pin_memory()
+    comp = make_components(K_CONCEPTS, args.variant, seed=args.seed, device=dev, dtype=dtype, masks=masks_host)
+    model = Tweediemix(namespace(args.variant), comp, variant=args.variant, use_cuda_graphs=not args.no_graphs,
+                       process_group=pg if group_size > 1 else None)
+    ns = model.config
+    if args.variant == "lora":
+        model.init_fusion(int(ns.n_timesteps * ns.t_cond), int(ns.n_timesteps * ns.t_stop))
+    else:
+        model.init_fusion(int(ns.n_timesteps * ns.t_cond))
+
+    gen = torch.Generator().manual_seed(args.seed + 17 * my_group)
+    x_host = torch.randn(1, 4, 128, 128, generator=gen).pin_memory()          # CPU-generator draw, like fusion_sampling.py:488
+    text_host, single_host = make_text(UNetConfig.sdxl_base(), K_CONCEPTS, args.seed + 1, dtype=dtype)
+    text_host = tuple(t.pin_memory() for t in text_host)
+    single_host = tuple(t.pin_memory() for t in single_host)
+    out_host = torch.empty(1, 4, 128, 128).pin_memory()
+    x_dev = x_host.to(dev)
+    fused_t = [t for t in model._timesteps if model.in_fused_phase(t)]
+
+    def step_resident():
+        if args.workload == "image50":
+            return model.sample_loop(x_dev)
+        return model.denoise_step(x_dev, fused_t[0])
+
+    def step_e2e():
+        model.set_masks(masks_host.to(dev, non_blocking=True))
+        model.set_text(tuple(t.to(dev, non_blocking=True) for t in text_host), tuple(t.to(dev, non_blocking=True) for t in single_host))
+        x = x_host.to(dev, non_blocking=True)
+        y = model.sample_loop(x) if args.workload == "image50" else model.denoise_step(x, fused_t[0])
+        out_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    h2d = masks_host.numel() * 4 + x_host.numel() * 4 + sum(t.numel() * t.element_size() for t in text_host + single_host)
+    d2h = out_host.numel() * 4
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    if args.ncu_range:
+        model.use_cuda_graphs = False
+        for _ in range(max(args.warmup, 1)):
+            model.denoise_step(x_dev, fused_t[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        model.denoise_step(x_dev, fused_t[1])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
+
+    for _ in range(args.warmup):
+        step_resident()
+    launches0 = ops.launch_count()
+    with ClockSampler(local) as clk:
+        total_ms = timed(step_resident, args.steps)
+    launches = ops.launch_count() - launches0
+    clocks = clk.summary()
+    step_e2e()                                           # warm (first set_text re-projects K/V)
+    e2e_ms = timed(step_e2e, args.steps)
+
+    units_per_step = n_groups                            # images (or fused steps) finished per benchmark step, whole job
+    ms_per_step = total_ms / args.steps
+    value = units_per_step * 1000.0 / ms_per_step
+    e2e_value = units_per_step * 1000.0 / (e2e_ms / args.steps)
+
+    # per-denoise-step ms of the fused phase (second half of the BASELINE metric)
+    n_f = 8
+    model.denoise_step(x_dev, fused_t[0])
+    fused_ms = timed(lambda: model.denoise_step(x_dev, fused_t[1]), n_f) / n_f
+
+    # ---- roofline of the hand-written kernels: instrumented EAGER fused step, CUDA events per launch
+    roof, others = None, []
+    pk = peaks()
+    graphs_were = model.use_cuda_graphs
+    model.use_cuda_graphs = False
+    model.denoise_step(x_dev, fused_t[1])                 # eager warm-up
+    prof = ops.KernelProfile()
+    ops.set_profile(prof)
+    model.denoise_step(x_dev, fused_t[1])
+    ops.set_profile(None)
+    model.use_cuda_graphs = graphs_were
+    summ = prof.summary()
+    fam = {}
+    for (f, tag), d in summ.items():
+        fam.setdefault(f, []).append((tag, d))
+    if "attention" in fam:
+        self_attn = [(tag, d) for tag, d in fam["attention"] if "Nk77" not in tag]
+        work = sum(d["work"] for _, d in self_attn); ms = sum(d["ms"] for _, d in self_attn); n = sum(d["launches"] for _, d in self_attn)
+        if ms > 0:
+            ach = work / (ms * 1e-3) / 1e12
+            roof = {"kernel": "attn_fwd_kernel (tcgen05 self-attention, all launches of one fused step)", "bound": "tensor",
+                    "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})", "traffic": None,
+                    "launches": n, "avg_launch_ms": ms / n, "flops_per_launch": work / n,
+                    "by_shape": {tag: {"launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
+                                       "tflops": d["work"] / (d["ms"] * 1e-3) / 1e12} for tag, d in fam["attention"]}}
+    for f in ("groupnorm", "resadd", "geglu", "blend"):
+        if f in fam:
+            work = sum(d["work"] for _, d in fam[f]); ms = sum(d["ms"] for _, d in fam[f]); n = sum(d["launches"] for _, d in fam[f])
+            if ms > 0:
+                gbs = work / (ms * 1e-3) / 1e9
+                others.append({"kernel": f, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                               "calls": n, "total_ms": ms})
+    step_kernel_ms = {f: sum(d["ms"] for _, d in v) for f, v in fam.items()}
+
+    # k7 at a size where HBM (not launch latency) is the bound: 2048 stacked images (2.5 GB)
+    try:
+        imgs = 2048
+        xb = torch.randn(imgs, 4, 128, 128, device=dev)
+        eb = torch.randn(imgs, K_CONCEPTS + 1, 4, 128, 128, device=dev, dtype=dtype)
+        mb = model.masks
+        ob = torch.empty_like(xb)
+        for _ in range(3):
+            ops.tweedie_blend_ddim(xb, eb, mb, 0.0438, 0.0518, 0.8, out=ob)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.tweedie_blend_ddim(xb, eb, mb, 0.0438, 0.0518, 0.8, out=ob)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        nbytes = imgs * (4 * 16384 * 8 + 4 * 4 * 16384 * eb.element_size()) + K_CONCEPTS * 16384 * 4
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        others.append({"kernel": "blend (k7) on 2048 stacked images", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                       "frac": gbs / pk["hbm"], "avg_launch_ms": ms, "bytes_per_launch": nbytes})
+        del xb, eb, ob
+    except Exception as e:                                 # never let the side measurement break the headline
+        others.append({"kernel": "blend (k7) on 2048 stacked images", "error": str(e)})
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle.cpu_baseline import CpuReference
+            torch.cuda.empty_cache()
+            ref = CpuReference(res=1024)
+            sec = ref.forward_seconds()
+            cpu = {"value": CpuReference.images_per_second(sec), "unit": "images/s", "cores": ref.threads, "kind": "port",
+                   "sample": ref.sample_description(), "seconds_per_sample_forward": sec}
+        except Exception as e:
+            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        metric = "1024px images/sec @50 DDIM steps, K concepts" if args.workload == "image50" else "fused denoise steps/sec (profiling workload)"
+        line = {"metric": metric, "value": value, "unit": "images/s" if args.workload == "image50" else "steps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": workload_config(args, group_size, n_groups),
+                "per_denoise_step_ms": fused_ms, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "images/s" if args.workload == "image50" else "steps/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "gpu_launches_by_kernel": {k: v for k, v in ops.LAUNCHES.items()},
+                "roofline": roof, "roofline_other": others, "fused_step_tmx_kernel_ms": step_kernel_ms,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

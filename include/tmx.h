@@ -91,18 +91,20 @@ TMX_API int tmx_tweedie_blend_ddim_fwd(const float* x, const void* eps, const fl
                                float a_t, float a_next, float g, int is_last,
                                int eps_dtype, int round_mode, void* stream);
 
-/* Concept-parallel (multi-GPU) split of k7, SURVEY §8e.  Linear form
- *   x0 = [ M x - s (1-g) M eps_u - s g sum_c m_c eps_c ] / sqrt(a_t),  M = sum_c m_c, s = sqrt(1-a_t)
- * partial: acc[img][0] (+)= sum_{rows r>0 owned} m_{c(r)} * eps_r ; acc[img][1] = eps_u if the
+/* Concept-parallel (multi-GPU) split of k7, SURVEY §8e.  Linear form (w_c = weights[c] or 1,
+ * m_c = masks[c] or 1):
+ *   x0 = [ M x - s (1-g) M eps_u - s g sum_c w_c m_c eps_c ] / sqrt(a_t),  M = sum_c w_c m_c, s = sqrt(1-a_t)
+ * partial: acc[img][0] = sum_{rows r>0 owned} w_{c(r)} m_{c(r)} * eps_r ; acc[img][1] = eps_u if the
  *          uncond row is owned else 0.  acc is fp32 [imgs, 2, C, HW] and is what gets all-reduced.
+ *          R may be 0 (a rank that owns no row of this phase contributes zeros).
  * finish : consumes the all-reduced acc and produces x_out / x0_out on every rank identically.
  * eps_rows : eps_dtype [imgs, R, C, HW] — only the R rows this rank computed;
  * row_ids  : HOST int[R], global row index of each local row (0 = uncond, 1+c = concept c).
  */
-TMX_API int tmx_blend_partial_fwd(const void* eps_rows, const float* masks, const int* row_ids,
-                          float* acc, int imgs, int R, int K, int C, int HW,
+TMX_API int tmx_blend_partial_fwd(const void* eps_rows, const float* masks, const float* weights,
+                          const int* row_ids, float* acc, int imgs, int R, int K, int C, int HW,
                           int eps_dtype, void* stream);
-TMX_API int tmx_blend_finish_fwd(const float* x, const float* acc, const float* masks,
+TMX_API int tmx_blend_finish_fwd(const float* x, const float* acc, const float* masks, const float* weights,
                          float* x_out, float* x0_out, int imgs, int K, int C, int HW,
                          float a_t, float a_next, float g, int is_last, void* stream);
 
@@ -129,6 +131,11 @@ TMX_API int    tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
  * also the three residual adds of BasicTransformerBlock).  n elements, n % 8 == 0; y may alias. */
 TMX_API int tmx_resadd_fwd(const void* a, const void* b, void* y, size_t n, float inv_scale,
                    int dtype, void* stream);
+
+/* k9a — GEGLU gating  y[m, j] = x[m, j] * gelu_erf(x[m, F + j])  ([D] diffusers GEGLU.forward inside
+ * BasicTransformerBlock.ff; 70 sites per U-Net forward).  x : dtype [rows, 2F], y : dtype [rows, F],
+ * fp16 / bf16, F % 8 == 0.  Algorithmic bytes: 3 * rows * F * sizeof(dtype). */
+TMX_API int tmx_geglu_fwd(const void* x, void* y, size_t rows, int F, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * k1 / k2 — scaled-dot-product attention forward, head dim 64, no mask, non-causal:

@@ -1,0 +1,97 @@
+"""TEST INFRASTRUCTURE ONLY: plain-PyTorch stand-ins for ``tweediemix_b200.ops`` so that the HOST
+logic of the product (U-Net wiring, hook routing, sampler phases, concept-parallel row assignment)
+can be exercised on the CPU-only build box against the oracle.  The product never imports this;
+``install(monkeypatch)`` swaps the functions in for one test.  The arithmetic of the blend functions
+is the oracle's (``oracle/step_math.py``), i.e. the checker, not the thing shipped.
+"""
+import torch
+import torch.nn.functional as F
+
+from oracle import step_math as sm
+
+
+def group_norm(x, gamma, beta, groups, eps, *, silu=False, add=None, out=None):
+    xf = x.float()
+    if add is not None:
+        xf = xf + add[:, :, None, None]
+    y = F.group_norm(xf, groups, gamma, beta, eps)
+    y = (F.silu(y) if silu else y).to(x.dtype)
+    y = y.contiguous(memory_format=torch.channels_last) if not x.is_contiguous() else y
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def residual_add(a, b, inv_scale=1.0, out=None):
+    y = ((a.float() + b.float()) * inv_scale).to(a.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def geglu(x, out=None):
+    h, g = x.chunk(2, dim=-1)
+    return h * F.gelu(g)
+
+
+def attention(q, k, v, heads, scale=None, out=None):
+    B, Nq, HD = q.shape
+    D = HD // heads
+    scale = D ** -0.5 if scale is None else scale
+    qh = q.reshape(B, Nq, heads, D).permute(0, 2, 1, 3).float()
+    kh = k.reshape(B, -1, heads, D).permute(0, 2, 1, 3).float()
+    vh = v.reshape(B, -1, heads, D).permute(0, 2, 1, 3).float()
+    p = (qh @ kh.transpose(-1, -2) * scale).softmax(dim=-1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(B, Nq, HD).to(q.dtype)
+
+
+def _mw(masks, weights, K, like):
+    m = masks if masks is not None else torch.ones(K, 1, 1, 1, device=like.device)
+    if weights is not None:
+        m = m * torch.tensor(weights, dtype=torch.float32, device=like.device).reshape(K, 1, 1, 1)
+    return m
+
+
+def tweedie_blend_ddim(x, eps, masks, a_t, a_next, g, *, is_last=False, weights=None, out=None, x0_out=None,
+                       ref_rounding=False):
+    C, H, W = x.shape[1:]
+    e = eps.reshape(-1, C, H, W).float()
+    K = e.shape[0] - 1
+    res, x0 = sm.fused_step(x, e, _mw(masks, weights, K, x), a_t, a_next, g, is_last=is_last)
+    if x0_out is not None:
+        x0_out.copy_(x0)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def blend_partial(eps_rows, masks, row_ids, acc, imgs=1, *, K=None, weights=None):
+    K = masks.shape[0] if K is None else K
+    mw = _mw(masks, weights, K, acc)
+    acc.zero_()
+    for j, r in enumerate(row_ids):
+        e = eps_rows.reshape(len(row_ids), *acc.shape[2:])[j].float()
+        if r == 0:
+            acc[0, 1] = e
+        else:
+            acc[0, 0] += mw[r - 1] * e
+    return acc
+
+
+def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_out=None, K=None, weights=None):
+    K = masks.shape[0] if K is None else K
+    M = _mw(masks, weights, K, x).sum(dim=0, keepdim=True).expand(1, 1, *x.shape[2:])
+    res, x0 = sm.blend_finish(x, acc[:, 0], acc[:, 1], M, a_t, a_next, g, is_last=is_last)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def install(monkeypatch):
+    from tweediemix_b200 import ops
+    for name in ("group_norm", "residual_add", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish"):
+        monkeypatch.setattr(ops, name, globals()[name])

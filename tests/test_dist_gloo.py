@@ -1,0 +1,73 @@
+"""CPU-only, world_size 2 over gloo: the concept-parallel path of the sampler (row assignment ->
+per-rank U-Net rows -> blend partial -> ONE all-reduce -> blend finish) gives every rank the latent
+the single-process sampler produces.  Kernels are the plain-PyTorch stand-ins of tests/fake_ops.py
+(host logic only; the real kernels run the same path in tests/test_gpu_model.py)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, lora, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_ops
+        from tweediemix_b200 import ops
+        for name in ("group_norm", "residual_add", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish"):
+            setattr(ops, name, getattr(fake_ops, name))
+        import test_host_logic as T
+        from oracle import synth
+        from oracle.hooks_ref import make_lora_set
+        n, res = 5, 128
+        ref_unet = synth.make_base_unet(T.RCFG, 1)
+        extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(T.K)] if lora else \
+                [synth.make_concept_unet(ref_unet, 10 + i) for i in range(T.K)]
+        s = T._product_sampler(ref_unet, extra, lora, n, res, pg=dist.group.WORLD)
+        s.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else s.init_fusion(int(n * 0.2))
+        torch.manual_seed(7)
+        x = s.sample_loop(torch.randn(1, 4, res // 8, res // 8))
+        torch.save({"x": x, "rows": s.n_forward_rows}, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_concept_parallel_two_ranks_equals_single(tmp_path, monkeypatch, lora):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), lora, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (torch.load(tmp_path / f"rank{r}.pt") for r in range(world))
+    assert torch.equal(r0["x"], r1["x"]), "ranks must end with bit-identical latents (no broadcast needed)"
+
+    sys.path.insert(0, HERE)
+    import fake_ops
+    import test_host_logic as T
+    from oracle import synth
+    from oracle.hooks_ref import make_lora_set
+    fake_ops.install(monkeypatch)
+    n, res = 5, 128
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(T.K)] if lora else \
+            [synth.make_concept_unet(ref_unet, 10 + i) for i in range(T.K)]
+    single = T._product_sampler(ref_unet, extra, lora, n, res)
+    single.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else single.init_fusion(int(n * 0.2))
+    torch.manual_seed(7)
+    want = single.sample_loop(torch.randn(1, 4, res // 8, res // 8))
+    # the sharded path evaluates the CFG / blend in its linear form (fp32): equal up to round-off
+    assert (r0["x"] - want).abs().max().item() < 2e-4
+    assert r0["rows"] + r1["rows"] == single.n_forward_rows      # every batch row computed exactly once

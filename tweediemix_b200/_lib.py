@@ -26,11 +26,12 @@ SIGNATURES = {
     "tmx_last_error": (C.c_char_p, []),
     "tmx_init": (_i, [_i]),
     "tmx_tweedie_blend_ddim_fwd": (_i, [_vp, _vp, _vp, C.POINTER(_f), _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp]),
-    "tmx_blend_partial_fwd": (_i, [_vp, _vp, C.POINTER(_i), _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "tmx_blend_finish_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _vp]),
+    "tmx_blend_partial_fwd": (_i, [_vp, _vp, C.POINTER(_f), C.POINTER(_i), _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "tmx_blend_finish_fwd": (_i, [_vp, _vp, _vp, C.POINTER(_f), _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _vp]),
     "tmx_groupnorm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tmx_groupnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "tmx_resadd_fwd": (_i, [_vp, _vp, _vp, _sz, _f, _i, _vp]),
+    "tmx_geglu_fwd": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
     "tmx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _f, _i, _vp]),
     "tmx_attn_set_variant": (_i, [_i]),
     "tmx_routed_linear_fwd": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -113,6 +113,7 @@ blend_kernel(const float* __restrict__ x, const T* __restrict__ eps, const float
 struct PartialRows {
     int n;
     int ids[kMaxConcepts + 1];
+    float w[kMaxConcepts + 1];        // weight of the concept each local row carries (unused for row id 0)
 };
 
 // One thread: one image, one channel, 8 pixels.  acc[img][0] = sum m_c eps_c ; acc[img][1] = eps_u or 0.
@@ -138,10 +139,16 @@ blend_partial_kernel(const T* __restrict__ eps_rows, const float* __restrict__ m
 #pragma unroll
             for (int i = 0; i < 8; ++i) u[i] = e[i];
         } else {
-            float m[8];
-            load8_f32_cached(masks + (size_t)(id - 1) * HW + p, m);
+            const float w = rows.w[r];
+            if (masks) {
+                float m[8];
+                load8_f32_cached(masks + (size_t)(id - 1) * HW + p, m);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = fmaf(m[i], e[i], a[i]);
+                for (int i = 0; i < 8; ++i) a[i] = fmaf(w * m[i], e[i], a[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = fmaf(w, e[i], a[i]);
+            }
         }
     }
     float* o = acc + (size_t)img * 2 * chw + (size_t)ch * HW + p;
@@ -163,10 +170,16 @@ blend_finish_kernel(const float* __restrict__ x, const float* __restrict__ acc, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) M[i] = 0.f;
     for (int c = 0; c < K; ++c) {
-        float m[8];
-        load8_f32_cached(masks + (size_t)c * HW + p, m);
+        const float w = cf.has_w ? cf.w[c] : 1.f;
+        if (masks) {
+            float m[8];
+            load8_f32_cached(masks + (size_t)c * HW + p, m);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) M[i] += m[i];
+            for (int i = 0; i < 8; ++i) M[i] = fmaf(w, m[i], M[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) M[i] += w;
+        }
     }
     const float k_u = cf.s_t * (1.f - cf.g), k_a = cf.s_t * cf.g;
     for (int ch = 0; ch < C; ++ch) {
@@ -241,10 +254,10 @@ extern "C" int tmx_tweedie_blend_ddim_fwd(const float* x, const void* eps, const
     return TMX_EDTYPE;
 }
 
-extern "C" int tmx_blend_partial_fwd(const void* eps_rows, const float* masks, const int* row_ids,
-                                     float* acc, int imgs, int R, int K, int C, int HW,
+extern "C" int tmx_blend_partial_fwd(const void* eps_rows, const float* masks, const float* weights,
+                                     const int* row_ids, float* acc, int imgs, int R, int K, int C, int HW,
                                      int eps_dtype, void* stream) {
-    TMX_REQUIRE(eps_rows && masks && row_ids && acc, TMX_EINVAL, "blend_partial: null pointer");
+    TMX_REQUIRE((eps_rows || R == 0) && (row_ids || R == 0) && acc, TMX_EINVAL, "blend_partial: null pointer");
     TMX_REQUIRE(imgs > 0 && C > 0 && HW > 0 && R >= 0, TMX_EINVAL, "blend_partial: bad size");
     TMX_REQUIRE(K >= 1 && K <= kMaxConcepts && R <= K + 1, TMX_ESHAPE, "blend_partial: K=%d R=%d unsupported", K, R);
     TMX_REQUIRE(HW % 8 == 0, TMX_ESHAPE, "blend_partial: HW=%d must be a multiple of 8", HW);
@@ -255,6 +268,7 @@ extern "C" int tmx_blend_partial_fwd(const void* eps_rows, const float* masks, c
     for (int r = 0; r < R; ++r) {
         TMX_REQUIRE(row_ids[r] >= 0 && row_ids[r] <= K, TMX_EINVAL, "blend_partial: row id %d outside [0,%d]", row_ids[r], K);
         rows.ids[r] = row_ids[r];
+        rows.w[r] = (weights && row_ids[r] > 0) ? weights[row_ids[r] - 1] : 1.f;
     }
     const long long total = (long long)imgs * C * (HW >> 3);
     const unsigned blocks = (unsigned)((total + 255) / 256);
@@ -268,10 +282,10 @@ extern "C" int tmx_blend_partial_fwd(const void* eps_rows, const float* masks, c
     return check_cuda(cudaGetLastError(), "blend_partial_kernel launch");
 }
 
-extern "C" int tmx_blend_finish_fwd(const float* x, const float* acc, const float* masks,
+extern "C" int tmx_blend_finish_fwd(const float* x, const float* acc, const float* masks, const float* weights,
                                     float* x_out, float* x0_out, int imgs, int K, int C, int HW,
                                     float a_t, float a_next, float g, int is_last, void* stream) {
-    TMX_REQUIRE(x && acc && masks && x_out, TMX_EINVAL, "blend_finish: null pointer");
+    TMX_REQUIRE(x && acc && x_out, TMX_EINVAL, "blend_finish: null pointer");
     TMX_REQUIRE(imgs > 0 && C > 0 && HW > 0, TMX_EINVAL, "blend_finish: non-positive size");
     TMX_REQUIRE(K >= 1 && K <= kMaxConcepts, TMX_ESHAPE, "blend_finish: K=%d unsupported", K);
     TMX_REQUIRE(HW % 8 == 0, TMX_ESHAPE, "blend_finish: HW=%d must be a multiple of 8", HW);
@@ -279,7 +293,7 @@ extern "C" int tmx_blend_finish_fwd(const float* x, const float* acc, const floa
                 TMX_EALIGN, "blend_finish: 16-byte alignment");
     TMX_REQUIRE(a_t > 0.f && a_t <= 1.f && a_next > 0.f && a_next <= 1.f, TMX_EINVAL, "blend_finish: bad alphas");
     if (int rc = require_init()) return rc;
-    BlendCoef cf = make_coef(a_t, a_next, g, is_last, nullptr, K);
+    BlendCoef cf = make_coef(a_t, a_next, g, is_last, weights, K);
     const long long total = (long long)imgs * (HW >> 3);
     const unsigned blocks = (unsigned)((total + 255) / 256);
     blend_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, acc, masks, x_out, x0_out, imgs, K, C, HW, cf);

@@ -45,6 +45,65 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+# ---- bookkeeping: how many tmx kernels were launched, and (optionally) how long each took ---------
+LAUNCHES = {}          # kernel family -> launches issued through this module (graph replays are added by the sampler)
+_profile = None        # a KernelProfile while bench.py's instrumented step runs
+
+
+def launch_count() -> int:
+    return sum(LAUNCHES.values())
+
+
+def add_launches(by_family: dict, times: int = 1) -> None:
+    for k, v in by_family.items():
+        LAUNCHES[k] = LAUNCHES.get(k, 0) + v * times
+
+
+class KernelProfile:
+    """CUDA-event timing of every tmx launch on the current stream (eager mode only).  ``work`` is the
+    algorithmic FLOPs (attention) or bytes (bandwidth kernels) of the launch, as defined in tmx.h."""
+
+    def __init__(self):
+        self.records = []          # (family, tag, work, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, tag, work, e0, e1 in self.records:
+            d = out.setdefault((fam, tag), {"launches": 0, "ms": 0.0, "work": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["work"] += work
+        return out
+
+
+def set_profile(p) -> None:
+    global _profile
+    _profile = p
+
+
+class _Launch:
+    """with _Launch(family, n_kernels, tag, work): <ctypes call>"""
+    __slots__ = ("fam", "n", "tag", "work", "e0")
+
+    def __init__(self, fam, n=1, tag="", work=0.0):
+        self.fam, self.n, self.tag, self.work = fam, n, tag, work
+
+    def __enter__(self):
+        LAUNCHES[self.fam] = LAUNCHES.get(self.fam, 0) + self.n
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profile.records.append((self.fam, self.tag, self.work, self.e0, e1))
+        return False
+
+
 # ------------------------------------------------------------------------------------------ k7
 
 def tweedie_blend_ddim(x, eps, masks, a_t: float, a_next: float, g: float, *, is_last=False,
@@ -67,36 +126,59 @@ def tweedie_blend_ddim(x, eps, masks, a_t: float, a_next: float, g: float, *, is
     if weights is not None:
         assert len(weights) == K
         w = (C.c_float * K)(*[float(v) for v in weights])
-    rc = _lib.load().tmx_tweedie_blend_ddim_fwd(
-        _p(x), _p(eps), _p(masks), w, _p(out), _p(x0_out), imgs, K, Cc, HW,
-        float(a_t), float(a_next), float(g), int(bool(is_last)), _dt(eps),
-        _lib.ROUND_REF if ref_rounding else _lib.ROUND_FP32, _stream())
+    nbytes = imgs * (Cc * HW * (8 + (4 if x0_out is not None else 0)) + (K + 1) * Cc * HW * eps.element_size()
+                     + (K * HW * 4 if masks is not None else 0))
+    with _Launch("blend", 1, f"imgs{imgs}_K{K}", nbytes):
+        rc = _lib.load().tmx_tweedie_blend_ddim_fwd(
+            _p(x), _p(eps), _p(masks), w, _p(out), _p(x0_out), imgs, K, Cc, HW,
+            float(a_t), float(a_next), float(g), int(bool(is_last)), _dt(eps),
+            _lib.ROUND_REF if ref_rounding else _lib.ROUND_FP32, _stream())
     _lib.check(rc, "tmx_tweedie_blend_ddim_fwd")
     return out
 
 
-def blend_partial(eps_rows, masks, row_ids, acc, imgs: int = 1):
-    """acc[img,0] = sum m_c eps_c over owned concept rows; acc[img,1] = eps_u if owned else 0."""
+def _wptr(weights, K):
+    if weights is None:
+        return None
+    assert len(weights) == K
+    return (C.c_float * K)(*[float(v) for v in weights])
+
+
+def blend_partial(eps_rows, masks, row_ids, acc, imgs: int = 1, *, K: int | None = None, weights=None):
+    """acc[img,0] = sum_c w_c m_c eps_c over the concept rows this rank owns; acc[img,1] = eps_u if the
+    uncond row (id 0) is owned else 0.  ``eps_rows`` [imgs, R, C, H, W] (or None when R == 0);
+    ``masks`` [K,1,H,W] fp32 or None (= ones); ``weights`` K host floats or None (= ones)."""
     _dev(eps_rows, masks, acc)
     R = len(row_ids)
-    Cc, HW = eps_rows.shape[-3], eps_rows.shape[-2] * eps_rows.shape[-1]
-    K = masks.shape[0]
-    assert acc.dtype == torch.float32 and acc.numel() == imgs * 2 * Cc * HW and acc.is_contiguous()
-    assert eps_rows.is_contiguous() and eps_rows.numel() == imgs * R * Cc * HW
+    assert acc.dtype == torch.float32 and acc.is_contiguous() and acc.dim() == 5 and acc.shape[0] == imgs and acc.shape[1] == 2
+    Cc, HW = acc.shape[2], acc.shape[3] * acc.shape[4]
+    if K is None:
+        assert masks is not None, "K is required when masks is None"
+        K = masks.shape[0]
+    if masks is not None:
+        assert masks.dtype == torch.float32 and masks.is_contiguous() and masks.numel() == K * HW
+    if R:
+        assert eps_rows.is_contiguous() and eps_rows.numel() == imgs * R * Cc * HW
     ids = (C.c_int * max(R, 1))(*[int(r) for r in row_ids])
-    rc = _lib.load().tmx_blend_partial_fwd(_p(eps_rows), _p(masks), ids, _p(acc), imgs, R, K, Cc, HW, _dt(eps_rows), _stream())
+    with _Launch("blend_partial"):
+        rc = _lib.load().tmx_blend_partial_fwd(_p(eps_rows) if R else None, _p(masks), _wptr(weights, K), ids, _p(acc),
+                                               imgs, R, K, Cc, HW, _dt(eps_rows) if R else _lib.F32, _stream())
     _lib.check(rc, "tmx_blend_partial_fwd")
     return acc
 
 
-def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_out=None):
+def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_out=None, K: int | None = None, weights=None):
+    """Every rank: finish from the all-reduced ``acc`` (bit-identical on all ranks)."""
     _dev(x, acc, masks, out, x0_out)
     imgs, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
-    K = masks.shape[0]
+    if K is None:
+        assert masks is not None, "K is required when masks is None"
+        K = masks.shape[0]
     if out is None:
         out = torch.empty_like(x)
-    rc = _lib.load().tmx_blend_finish_fwd(_p(x), _p(acc), _p(masks), _p(out), _p(x0_out), imgs, K, Cc, HW,
-                                          float(a_t), float(a_next), float(g), int(bool(is_last)), _stream())
+    with _Launch("blend_finish"):
+        rc = _lib.load().tmx_blend_finish_fwd(_p(x), _p(acc), _p(masks), _wptr(weights, K), _p(out), _p(x0_out), imgs, K, Cc, HW,
+                                              float(a_t), float(a_next), float(g), int(bool(is_last)), _stream())
     _lib.check(rc, "tmx_blend_finish_fwd")
     return out
 
@@ -109,7 +191,9 @@ _gn_ws = {}
 def _workspace(dev: int, nbytes: int) -> torch.Tensor:
     ws = _gn_ws.get(dev)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=f"cuda:{dev}")
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("tmx: GroupNorm workspace would have to grow during CUDA-graph capture; run the op once eagerly first")
+        ws = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=f"cuda:{dev}")
         _gn_ws[dev] = ws
     return ws
 
@@ -133,8 +217,9 @@ def group_norm(x, gamma, beta, groups: int, eps: float, *, silu=False, add=None,
         assert add.dtype == torch.float32 and add.is_contiguous() and add.shape == (N, Cc)
     lib = _lib.load()
     ws = _workspace(d, lib.tmx_groupnorm_workspace_bytes(N, Cc, H * W, groups, layout))
-    rc = lib.tmx_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(add), _p(out), _p(ws), N, Cc, H * W, groups,
-                               float(eps), _lib.ACT_SILU if silu else _lib.ACT_NONE, layout, _dt(x), _stream())
+    with _Launch("groupnorm", 2, f"C{Cc}_HW{H * W}", 2.0 * x.numel() * x.element_size()):
+        rc = lib.tmx_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(add), _p(out), _p(ws), N, Cc, H * W, groups,
+                                   float(eps), _lib.ACT_SILU if silu else _lib.ACT_NONE, layout, _dt(x), _stream())
     _lib.check(rc, "tmx_groupnorm_fwd")
     return out
 
@@ -148,8 +233,24 @@ def residual_add(a, b, inv_scale: float = 1.0, out=None):
     if out is None:
         out = torch.empty_like(a)
     assert out.stride() == a.stride()
-    rc = _lib.load().tmx_resadd_fwd(_p(a), _p(b), _p(out), a.numel(), float(inv_scale), _dt(a), _stream())
+    with _Launch("resadd", 1, "", 3.0 * a.numel() * a.element_size()):
+        rc = _lib.load().tmx_resadd_fwd(_p(a), _p(b), _p(out), a.numel(), float(inv_scale), _dt(a), _stream())
     _lib.check(rc, "tmx_resadd_fwd")
+    return out
+
+
+def geglu(x, out=None):
+    """x [..., 2F] -> x[..., :F] * gelu(x[..., F:]) (exact erf GELU); fp16 / bf16."""
+    _dev(x, out)
+    assert x.is_contiguous()
+    F2 = x.shape[-1]
+    assert F2 % 2 == 0
+    rows = x.numel() // F2
+    if out is None:
+        out = torch.empty(*x.shape[:-1], F2 // 2, dtype=x.dtype, device=x.device)
+    with _Launch("geglu", 1, "", 1.5 * x.numel() * x.element_size()):
+        rc = _lib.load().tmx_geglu_fwd(_p(x), _p(out), rows, F2 // 2, _dt(x), _stream())
+    _lib.check(rc, "tmx_geglu_fwd")
     return out
 
 
@@ -170,8 +271,9 @@ def attention(q, k, v, heads: int, scale: float | None = None, out=None):
         out = torch.empty((B, Nq, HD), dtype=q.dtype, device=q.device)
     if scale is None:
         scale = D ** -0.5
-    rc = _lib.load().tmx_attn_fwd(_p(q), _p(k), _p(v), _p(out), B, heads, Nq, Nk, D,
-                                  q.stride(1), k.stride(1), v.stride(1), out.stride(1),
-                                  float(scale), _dt(q), _stream())
+    with _Launch("attention", 1, f"Nq{Nq}_Nk{Nk}_H{heads}", 4.0 * B * heads * Nq * Nk * D):
+        rc = _lib.load().tmx_attn_fwd(_p(q), _p(k), _p(v), _p(out), B, heads, Nq, Nk, D,
+                                      q.stride(1), k.stride(1), v.stride(1), out.stride(1),
+                                      float(scale), _dt(q), _stream())
     _lib.check(rc, "tmx_attn_fwd")
     return out

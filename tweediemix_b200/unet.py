@@ -1,0 +1,549 @@
+"""SDXL-base ``UNet2DConditionModel`` executed B200-first (host side of the hot path).
+
+The reference drives diffusers' U-Net (``fusion_generation/fusion_sampling.py:340``:
+``self.unet(latent, t, encoder_hidden_states=E, added_cond_kwargs={...})['sample']``) and patches
+its ``Attention`` modules (``utils_custom.py:45-158`` / ``utils_lora.py:47-218``).  diffusers is not
+part of this image, so this module provides the same *surface* — module tree, attribute names
+(``down_blocks[i].attentions[j].transformer_blocks[k].attn{1,2}.to_{q,k,v}`` / ``.to_out[0]``,
+``resnets[j].norm1/conv1/time_emb_proj/norm2/conv2/conv_shortcut`` ...), state-dict keys and call
+signature of diffusers 0.29.2 for the ``stabilityai/stable-diffusion-xl-base-1.0`` config — so that
+SDXL / Custom-Diffusion / LoRA checkpoints load by name and the hook API applies unchanged, while
+the execution is laid out for B200:
+
+  * activations stay NHWC (``channels_last``) in bf16/fp16 end to end: the ``[B, HW, C]`` token view
+    the transformer blocks need is the same memory, so the reference's NCHW<->token permutes vanish;
+  * GroupNorm(+temb add)(+SiLU), the ResNet / transformer residual adds, GEGLU gating and all
+    attention (self and cross) run in the hand-written sm_100a kernels of ``libtmx.so`` (``ops``);
+  * self-attention Q/K/V come from ONE packed projection whose output is consumed in place by the
+    attention kernel through strided TMA descriptors (no split / permute / head reshape);
+  * cross-attention K/V depend only on the text embeddings, which are constant over the 50 steps
+    (``fusion_sampling.py:312-336``), so they are projected once per prompt set — with per-row
+    concept weights when routing is active — and cached; the per-step work is the Q projection only;
+  * the 17 ``time_emb_proj`` GEMVs are one packed GEMM per forward;
+  * nothing in ``forward`` reads device data on the host, so a whole step is CUDA-graph capturable.
+
+Dense GEMMs / convolutions that the north star leaves to libraries go to cuBLASLt / cuDNN through
+``torch.nn.functional`` (plumbing).  There is no PyTorch fallback for the tmx ops: a missing
+``libtmx.so`` or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+@dataclass
+class UNetConfig:
+    """The subset of ``unet/config.json`` that shapes the SDXL-base U-Net."""
+    in_channels: int = 4
+    out_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280)
+    layers_per_block: int = 2
+    transformer_layers_per_block: Tuple[int, ...] = (1, 2, 10)
+    attention_head_dim: Tuple[int, ...] = (5, 10, 20)        # diffusers' name; these are head COUNTS
+    cross_attention_dim: int = 2048
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+    addition_time_embed_dim: int = 256
+    projection_class_embeddings_input_dim: int = 2816
+    down_block_has_attention: Tuple[bool, ...] = (False, True, True)
+    up_block_has_attention: Tuple[bool, ...] = (True, True, False)
+
+    @property
+    def time_embed_dim(self) -> int:
+        return 4 * self.block_out_channels[0]
+
+    @property
+    def pooled_dim(self) -> int:
+        return self.projection_class_embeddings_input_dim - 6 * self.addition_time_embed_dim
+
+    @classmethod
+    def sdxl_base(cls) -> "UNetConfig":
+        return cls()
+
+    @classmethod
+    def narrow(cls, width: int = 64, cross_dim: int = 128, pooled: int = 64, add_dim: int = 32) -> "UNetConfig":
+        """Same topology as SDXL-base (17 ResNets, 70 transformer blocks, head dim 64) at toy width."""
+        return cls(block_out_channels=(width, 2 * width, 4 * width),
+                   attention_head_dim=(width // 64, 2 * width // 64, 4 * width // 64),
+                   cross_attention_dim=cross_dim, addition_time_embed_dim=add_dim,
+                   projection_class_embeddings_input_dim=pooled + 6 * add_dim)
+
+
+HEAD_DIM = 64
+
+
+def _tokens(x4: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] channels_last  ->  [B, HW, C] view of the same memory."""
+    b, c, h, w = x4.shape
+    return x4.permute(0, 2, 3, 1).reshape(b, h * w, c)
+
+
+def _image(x3: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """[B, HW, C] -> [B,C,H,W] channels_last view of the same memory."""
+    b, _, c = x3.shape
+    return x3.reshape(b, h, w, c).permute(0, 3, 1, 2)
+
+
+class TmxGroupNorm(nn.GroupNorm):
+    """``nn.GroupNorm`` parameters (state-dict names ``weight`` / ``bias``) executed by k4/k5."""
+
+    def __init__(self, groups: int, channels: int, eps: float):
+        super().__init__(groups, channels, eps=eps, affine=True)
+        self._w32: Optional[torch.Tensor] = None
+        self._b32: Optional[torch.Tensor] = None
+
+    def _params32(self):
+        if self._w32 is None or self._w32.device != self.weight.device:
+            self._w32 = self.weight.detach().float().contiguous()
+            self._b32 = self.bias.detach().float().contiguous()
+        return self._w32, self._b32
+
+    def forward(self, x, silu: bool = False, add: Optional[torch.Tensor] = None):  # type: ignore[override]
+        w, b = self._params32()
+        return ops.group_norm(x, w, b, self.num_groups, self.eps, silu=silu, add=add)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_dim: int, out_dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_dim, out_dim)
+        self.linear_2 = nn.Linear(out_dim, out_dim)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+def sinusoid(values: torch.Tensor, dim: int) -> torch.Tensor:
+    """[D] ``get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0)``: [cos | sin]."""
+    half = dim // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=values.device) * (-math.log(10000.0) / half))
+    arg = values.reshape(-1, 1).float() * freq
+    return torch.cat([arg.cos(), arg.sin()], dim=-1)
+
+
+# =============================================================================== attention
+
+class TmxAttention(nn.Module):
+    """diffusers ``Attention`` surface (``to_q/to_k/to_v/to_out``, ``heads``, ``scale``) on the tcgen05
+    attention kernel.  ``routing`` is installed by the hook layer (``utils_custom`` / ``utils_lora``)."""
+
+    def __init__(self, query_dim: int, heads: int, cross_attention_dim: Optional[int] = None):
+        super().__init__()
+        inner = heads * HEAD_DIM
+        self.heads = heads
+        self.scale = HEAD_DIM ** -0.5
+        self.is_cross = cross_attention_dim is not None
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)
+        self.to_v = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(0.0)])
+        self._w_qkv: Optional[torch.Tensor] = None          # packed [3*inner, query_dim] (self-attn)
+        self._w_kv: Optional[torch.Tensor] = None           # packed [2*inner, cross_dim]  (cross-attn)
+        self._kv_cache = {}                                 # key -> (ehs tensor, routed, kv [B,Nk,2*inner])
+
+    # ---- packed weights -------------------------------------------------------------------
+    def packed_qkv(self) -> torch.Tensor:
+        if self._w_qkv is None or self._w_qkv.device != self.to_q.weight.device or self._w_qkv.dtype != self.to_q.weight.dtype:
+            self._w_qkv = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight]).detach().contiguous()
+        return self._w_qkv
+
+    def packed_kv(self) -> torch.Tensor:
+        if self._w_kv is None or self._w_kv.device != self.to_k.weight.device or self._w_kv.dtype != self.to_k.weight.dtype:
+            self._w_kv = torch.cat([self.to_k.weight, self.to_v.weight]).detach().contiguous()
+        return self._w_kv
+
+    def drop_packed(self):
+        self._w_qkv = self._w_kv = None
+        self._kv_cache.clear()
+
+    # ---- hook-facing helpers --------------------------------------------------------------
+    def head_to_batch_dim(self, t):          # kept for API parity; the tmx kernel never needs it
+        b, n, c = t.shape
+        return t.reshape(b, n, self.heads, c // self.heads).permute(0, 2, 1, 3).reshape(b * self.heads, n, c // self.heads)
+
+    def batch_to_head_dim(self, t):
+        bh, n, d = t.shape
+        b = bh // self.heads
+        return t.reshape(b, self.heads, n, d).permute(0, 2, 1, 3).reshape(b, n, self.heads * d)
+
+    # ---- cross-attention K/V (text-only, step-invariant) ------------------------------------
+    def _project_kv(self, ehs: torch.Tensor, routing) -> torch.Tensor:
+        """[B, Nk, 2*inner] = (K | V).  ``routing`` = None, or an object with ``kv_rows(attn, ehs)``."""
+        if routing is None:
+            return F.linear(ehs, self.packed_kv())
+        return routing.kv_rows(self, ehs)
+
+    @staticmethod
+    def _kv_key(ehs, routing):
+        # the entry keeps `ehs` alive (its address cannot be recycled) and `_version` catches in-place edits
+        return (ehs.data_ptr(), tuple(ehs.shape), ehs._version, None if routing is None else routing.cache_tag)
+
+    def cross_kv(self, ehs: torch.Tensor, routing) -> torch.Tensor:
+        key = self._kv_key(ehs, routing)
+        hit = self._kv_cache.get(key)
+        if hit is None:
+            if len(self._kv_cache) >= 16:                   # callers that stream fresh tensors: drop the oldest
+                self._kv_cache.pop(next(iter(self._kv_cache)))
+            kv = self._project_kv(ehs, routing)
+            self._kv_cache[key] = (ehs, routing, kv)
+            return kv
+        return hit[2]
+
+    def refresh_kv_cache(self):
+        """Recompute every cached K/V *into its existing storage* (CUDA graphs keep pointing at it)
+        after the text-embedding buffers were overwritten in place."""
+        entries = list(self._kv_cache.values())
+        self._kv_cache.clear()
+        for ehs, routing, kv in entries:
+            kv.copy_(self._project_kv(ehs, routing))
+            self._kv_cache[self._kv_key(ehs, routing)] = (ehs, routing, kv)
+
+    # ---- the op ---------------------------------------------------------------------------
+    def run(self, x: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None, routing=None,
+            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """q/k/v projections -> SDPA -> ``to_out[0]`` (``utils_custom.py:64-106``), plus the optional
+        rank-r routed deltas of ``utils_lora.py:65-79,113-121``.  ``residual`` (same shape as the
+        output) is added by the fused k6 kernel."""
+        inner = self.heads * HEAD_DIM
+        lora = routing if (routing is not None and routing.kind == "lora") else None
+        if encoder_hidden_states is None:
+            qkv = F.linear(x, self.packed_qkv())                                  # [B, N, 3*inner]
+            if lora is not None:
+                lora.add_qkv_self(self, x, qkv)
+            q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
+        else:
+            q = F.linear(x, self.to_q.weight)
+            if lora is not None:
+                lora.add_q(self, x, q)
+            kv = self.cross_kv(encoder_hidden_states, routing)
+            k, v = kv[..., :inner], kv[..., inner:]
+        a = ops.attention(q, k, v, self.heads, self.scale)                        # [B, N, inner]
+        o = F.linear(a, self.to_out[0].weight, self.to_out[0].bias)
+        if lora is not None:
+            lora.add_out(self, a, o)
+        if residual is not None:
+            o = ops.residual_add(o, residual, out=o)
+        return o
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, residual=None):
+        if attention_mask is not None:
+            raise RuntimeError("tmx attention has no mask path (the reference never passes one: utils_custom.py:95-99 is dead code)")
+        return self.run(hidden_states, encoder_hidden_states, None, residual)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        return ops.geglu(self.proj(x))
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int, mult: int = 4):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+    def forward(self, x):
+        return self.net[2](self.net[0](x))
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim: int, heads: int, cross_attention_dim: int):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn1 = TmxAttention(dim, heads, None)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn2 = TmxAttention(dim, heads, cross_attention_dim)
+        self.norm3 = nn.LayerNorm(dim, eps=1e-5)
+        self.ff = FeedForward(dim)
+
+    @staticmethod
+    def _ln(norm: nn.LayerNorm, h):
+        return F.layer_norm(h, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
+
+    @staticmethod
+    def _call_attn(attn: TmxAttention, x, ehs, residual):
+        # A hooked module carries an instance-level ``forward`` with the reference's 3-argument
+        # signature (utils_custom.py:53); the residual is then added here instead of inside.
+        hooked = attn.__dict__.get("forward")
+        if hooked is None:
+            return attn(x, encoder_hidden_states=ehs, attention_mask=None, residual=residual)
+        o = hooked(x, encoder_hidden_states=ehs, attention_mask=None)
+        return ops.residual_add(o, residual, out=o)
+
+    def forward(self, h, encoder_hidden_states):
+        h = self._call_attn(self.attn1, self._ln(self.norm1, h), None, h)
+        h = self._call_attn(self.attn2, self._ln(self.norm2, h), encoder_hidden_states, h)
+        f = self.ff(self._ln(self.norm3, h))
+        return ops.residual_add(f, h, out=f)
+
+
+class Transformer2DModel(nn.Module):
+    """``use_linear_projection=True`` variant; NHWC in, NHWC out, no permutes."""
+
+    def __init__(self, channels: int, heads: int, depth: int, cross_attention_dim: int, groups: int):
+        super().__init__()
+        self.norm = TmxGroupNorm(groups, channels, eps=1e-6)
+        self.proj_in = nn.Linear(channels, channels)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(channels, heads, cross_attention_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(channels, channels)
+
+    def forward(self, x, encoder_hidden_states):
+        _, _, hh, ww = x.shape
+        h = self.proj_in(_tokens(self.norm(x, silu=False)))
+        for blk in self.transformer_blocks:
+            h = blk(h, encoder_hidden_states)
+        h = _image(self.proj_out(h), hh, ww)
+        return ops.residual_add(h, x, out=h)
+
+
+# =============================================================================== ResNet / sampling blocks
+
+class ResnetBlock2D(nn.Module):
+    """[D] ``ResnetBlock2D`` (body mirrored in the reference at ``video_gen/utils_attn.py:391-431``):
+    GN+SiLU -> conv1 -> (+temb) GN+SiLU -> conv2 -> (+shortcut(x)) / output_scale_factor."""
+
+    def __init__(self, cin: int, cout: int, temb_dim: int, groups: int, eps: float):
+        super().__init__()
+        self.norm1 = TmxGroupNorm(groups, cin, eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_dim, cout)
+        self.norm2 = TmxGroupNorm(groups, cout, eps)
+        self.dropout = nn.Dropout(0.0)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+        self.output_scale_factor = 1.0
+        self.temb_slice_index = 0                           # set by the U-Net: which split of the packed temb GEMM
+
+    def forward(self, x, temb_all):
+        h = self.conv1(self.norm1(x, silu=True))
+        h = self.conv2(self.norm2(h, silu=True, add=temb_all[self.temb_slice_index]))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return ops.residual_add(h, x, 1.0 / self.output_scale_factor, out=h)
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class DownBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, cin, cout, depth, heads, has_attn, add_down):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlock2D(cin if i == 0 else cout, cout, cfg.time_embed_dim, cfg.norm_num_groups, cfg.norm_eps)
+            for i in range(cfg.layers_per_block)])
+        self.attentions = nn.ModuleList([
+            Transformer2DModel(cout, heads, depth, cfg.cross_attention_dim, cfg.norm_num_groups)
+            for _ in range(cfg.layers_per_block)]) if has_attn else None
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
+
+    def forward(self, h, temb_all, ehs, skips):
+        for i, res in enumerate(self.resnets):
+            h = res(h, temb_all)
+            if self.attentions is not None:
+                h = self.attentions[i](h, ehs)
+            skips.append(h)
+        if self.downsamplers is not None:
+            h = self.downsamplers[0](h)
+            skips.append(h)
+        return h
+
+
+class MidBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, c, depth, heads):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlock2D(c, c, cfg.time_embed_dim, cfg.norm_num_groups, cfg.norm_eps) for _ in range(2)])
+        self.attentions = nn.ModuleList([Transformer2DModel(c, heads, depth, cfg.cross_attention_dim, cfg.norm_num_groups)])
+
+    def forward(self, h, temb_all, ehs):
+        h = self.resnets[0](h, temb_all)
+        h = self.attentions[0](h, ehs)
+        return self.resnets[1](h, temb_all)
+
+
+class UpBlock(nn.Module):
+    def __init__(self, cfg: UNetConfig, c_skip_last, cout, c_prev, depth, heads, has_attn, add_up):
+        super().__init__()
+        n = cfg.layers_per_block + 1
+        self.resnets = nn.ModuleList([
+            ResnetBlock2D((c_prev if i == 0 else cout) + (c_skip_last if i == n - 1 else cout), cout,
+                          cfg.time_embed_dim, cfg.norm_num_groups, cfg.norm_eps) for i in range(n)])
+        self.attentions = nn.ModuleList([
+            Transformer2DModel(cout, heads, depth, cfg.cross_attention_dim, cfg.norm_num_groups)
+            for _ in range(n)]) if has_attn else None
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
+
+    def forward(self, h, temb_all, ehs, skips):
+        for i, res in enumerate(self.resnets):
+            h = res(torch.cat([h, skips.pop()], dim=1), temb_all)
+            if self.attentions is not None:
+                h = self.attentions[i](h, ehs)
+        if self.upsamplers is not None:
+            h = self.upsamplers[0](h)
+        return h
+
+
+# =============================================================================== the U-Net
+
+class TmxUNet2DConditionModel(nn.Module):
+    """Call surface of ``fusion_sampling.py:340``.  Inputs may be NCHW-contiguous fp32 (as the
+    reference's sampler holds ``x``); the output ``['sample']`` is ``[B, 4, H, W]`` in the model dtype."""
+
+    def __init__(self, cfg: Optional[UNetConfig] = None):
+        super().__init__()
+        cfg = cfg or UNetConfig.sdxl_base()
+        self.cfg = cfg
+        boc = cfg.block_out_channels
+        self.conv_in = nn.Conv2d(cfg.in_channels, boc[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(boc[0], cfg.time_embed_dim)
+        self.add_embedding = TimestepEmbedding(cfg.projection_class_embeddings_input_dim, cfg.time_embed_dim)
+
+        self.down_blocks = nn.ModuleList()
+        cout = boc[0]
+        for i, c in enumerate(boc):
+            cin, cout = cout, c
+            self.down_blocks.append(DownBlock(cfg, cin, cout, cfg.transformer_layers_per_block[i],
+                                              cfg.attention_head_dim[i], cfg.down_block_has_attention[i],
+                                              add_down=i + 1 < len(boc)))
+        self.mid_block = MidBlock(cfg, boc[-1], cfg.transformer_layers_per_block[-1], cfg.attention_head_dim[-1])
+        self.up_blocks = nn.ModuleList()
+        rev, rdepth, rheads = boc[::-1], cfg.transformer_layers_per_block[::-1], cfg.attention_head_dim[::-1]
+        cout = rev[0]
+        for i, c in enumerate(rev):
+            c_prev, cout = cout, c
+            self.up_blocks.append(UpBlock(cfg, rev[min(i + 1, len(boc) - 1)], cout, c_prev, rdepth[i], rheads[i],
+                                          cfg.up_block_has_attention[i], add_up=i + 1 < len(boc)))
+        self.conv_norm_out = TmxGroupNorm(cfg.norm_num_groups, boc[0], cfg.norm_eps)
+        self.conv_out = nn.Conv2d(boc[0], cfg.out_channels, 3, padding=1)
+
+        self._resnets = [m for m in self.modules() if isinstance(m, ResnetBlock2D)]
+        for i, r in enumerate(self._resnets):
+            r.temb_slice_index = i
+        self._temb_w: Optional[torch.Tensor] = None
+        self._temb_b: Optional[torch.Tensor] = None
+        self._temb_splits = [r.time_emb_proj.out_features for r in self._resnets]
+
+    # ---- structure helpers ------------------------------------------------------------------
+    def attention_modules(self):
+        """Yield (qualified name, TmxAttention) for all 140 attention modules."""
+        for name, m in self.named_modules():
+            if isinstance(m, TmxAttention):
+                yield name, m
+
+    def transformer_blocks(self):
+        for name, m in self.named_modules():
+            if isinstance(m, BasicTransformerBlock):
+                yield name, m
+
+    @property
+    def device(self):
+        return self.conv_in.weight.device
+
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+    def finalize(self):
+        """Call after loading / moving weights: convs to channels_last, packed weights rebuilt lazily."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+            elif isinstance(m, TmxAttention):
+                m.drop_packed()
+            elif isinstance(m, TmxGroupNorm):
+                m._w32 = m._b32 = None
+        self._temb_w = self._temb_b = None
+        return self
+
+    def refresh_text_cache(self):
+        for _, m in self.attention_modules():
+            if m.is_cross:
+                m.refresh_kv_cache()
+
+    def clear_text_cache(self):
+        for _, m in self.attention_modules():
+            m._kv_cache.clear()
+
+    # ---- forward --------------------------------------------------------------------------
+    def _packed_temb(self):
+        if self._temb_w is None or self._temb_w.device != self.device or self._temb_w.dtype != self.dtype:
+            self._temb_w = torch.cat([r.time_emb_proj.weight for r in self._resnets]).detach().contiguous()
+            self._temb_b = torch.cat([r.time_emb_proj.bias for r in self._resnets]).detach().contiguous()
+        return self._temb_w, self._temb_b
+
+    def embed(self, batch: int, timestep, added_cond_kwargs) -> torch.Tensor:
+        dev, dt = self.device, self.dtype
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
+        t = timestep.to(dev).reshape(-1).expand(batch)
+        emb = self.time_embedding(sinusoid(t, self.cfg.block_out_channels[0]).to(dt))
+        tid = sinusoid(added_cond_kwargs["time_ids"].to(dev).flatten(), self.cfg.addition_time_embed_dim).reshape(batch, -1)
+        add = torch.cat([added_cond_kwargs["text_embeds"].to(dev, dt), tid.to(dt)], dim=-1)
+        return emb + self.add_embedding(add)
+
+    def forward(self, sample, timestep, encoder_hidden_states, added_cond_kwargs):
+        dt = self.dtype
+        b = sample.shape[0]
+        temb = self.embed(b, timestep, added_cond_kwargs)
+        w, bias = self._packed_temb()
+        # one GEMM for all 17 time_emb_proj; fp32 per-(n,c) biases consumed by the GN kernel's `add`
+        temb_all = [t.contiguous() for t in F.linear(F.silu(temb), w, bias).float().split(self._temb_splits, dim=1)]
+        ehs = encoder_hidden_states if encoder_hidden_states.dtype == dt else encoder_hidden_states.to(dt)
+        h = self.conv_in(sample.to(dt).contiguous(memory_format=torch.channels_last))
+        skips = [h]
+        for blk in self.down_blocks:
+            h = blk(h, temb_all, ehs, skips)
+        h = self.mid_block(h, temb_all, ehs)
+        for blk in self.up_blocks:
+            h = blk(h, temb_all, ehs, skips)
+        h = self.conv_out(self.conv_norm_out(h, silu=True))
+        return {"sample": h.contiguous()}
+
+
+def init_synthetic_(unet: nn.Module, seed: int, branch_damp: float = 0.3, device=None) -> nn.Module:
+    """Seeded random weights for benchmarking when no SDXL checkpoint is reachable (there is no
+    network on the GPU box): fan-in-scaled normals, residual-branch output projections damped so
+    activations stay O(1) through 70 transformer blocks and 50 steps.  Drawn with the
+    generator of the parameter's own device (fast for the 2.6 B-parameter real config)."""
+    gens = {}
+    for name, p in sorted(unet.named_parameters(), key=lambda kv: kv[0]):
+        g = gens.get(p.device)
+        if g is None:
+            g = gens[p.device] = torch.Generator(device=p.device).manual_seed(seed)
+        with torch.no_grad():
+            if p.ndim == 1:
+                r = torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32)
+                p.copy_((r * 0.02) if name.endswith("bias") else (1.0 + r * 0.05))
+                continue
+            std = p[0].numel() ** -0.5
+            if name.endswith(("to_out.0.weight", "ff.net.2.weight", "conv2.weight", "proj_out.weight")):
+                std *= branch_damp
+            p.copy_(torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32) * std)
+    return unet
