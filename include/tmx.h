@@ -132,6 +132,12 @@ TMX_API int    tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
 TMX_API int tmx_resadd_fwd(const void* a, const void* b, void* y, size_t n, float inv_scale,
                    int dtype, void* stream);
 
+/* k8 — LayerNorm over the last dimension ([D] BasicTransformerBlock.norm1/2/3 = F.layer_norm, fp32
+ * statistics; 210 sites per U-Net forward).  x, y : dtype [rows, D] (y may alias x); gamma, beta : fp32 [D].
+ * fp16 / bf16, D % 8 == 0, D <= 2048.  One pass: algorithmic bytes 2 * rows * D * sizeof(dtype). */
+TMX_API int tmx_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
+                      size_t rows, int D, float eps, int dtype, void* stream);
+
 /* k9a — GEGLU gating  y[m, j] = x[m, j] * gelu_erf(x[m, F + j])  ([D] diffusers GEGLU.forward inside
  * BasicTransformerBlock.ff; 70 sites per U-Net forward).  x : dtype [rows, 2F], y : dtype [rows, F],
  * fp16 / bf16, F % 8 == 0.  Algorithmic bytes: 3 * rows * F * sizeof(dtype). */

@@ -31,6 +31,10 @@ def residual_add(a, b, inv_scale=1.0, out=None):
     return y
 
 
+def layer_norm(x, gamma, beta, eps, out=None):
+    return F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps).to(x.dtype)
+
+
 def geglu(x, out=None):
     h, g = x.chunk(2, dim=-1)
     return h * F.gelu(g)
@@ -93,5 +97,5 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
 
 def install(monkeypatch):
     from tweediemix_b200 import ops
-    for name in ("group_norm", "residual_add", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish"):
+    for name in ("group_norm", "layer_norm", "residual_add", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -205,3 +205,29 @@ def test_residual_add(dtype):
             assert torch.equal(got, want)
     with pytest.raises(RuntimeError, match="multiple of 8"):
         o.residual_add(torch.zeros(7).cuda(), torch.zeros(7).cuda())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 4096, 640), (4, 1024, 1280), (3, 5, 64), (1, 1, 8), (2, 7, 2048), (9, 1000)])
+def test_layernorm_matches_fp32_reference(dtype, shape):
+    """k8 vs F.layer_norm evaluated in fp32 on the same 16-bit input: one rounding of the output dtype."""
+    o = ops()
+    g = torch.Generator().manual_seed(shape[-1])
+    x = (torch.randn(shape, generator=g) * 2.0 + 3.0).to(dtype)
+    D = shape[-1]
+    gamma, beta = 1 + 0.3 * torch.randn(D, generator=g), 0.2 * torch.randn(D, generator=g)
+    want = F.layer_norm(x.float(), (D,), gamma, beta, 1e-5)
+    got = o.layer_norm(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5)
+    torch.testing.assert_close(got.cpu().float(), want.to(dtype).float(),
+                               rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
+    xc = x.cuda()
+    o.layer_norm(xc, gamma.cuda(), beta.cuda(), 1e-5, out=xc)          # in place
+    assert torch.equal(xc.cpu(), got.cpu())
+
+
+def test_layernorm_errors():
+    o = ops()
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        o.layer_norm(torch.zeros(2, 12, dtype=torch.bfloat16).cuda(), torch.ones(12).cuda(), torch.zeros(12).cuda(), 1e-5)
+    with pytest.raises(RuntimeError, match="<= 2048"):
+        o.layer_norm(torch.zeros(2, 4096, dtype=torch.bfloat16).cuda(), torch.ones(4096).cuda(), torch.zeros(4096).cuda(), 1e-5)

@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Micro-benchmark of every tmx kernel at the shapes one K=3 fused step of SDXL 1024² launches them with.
+
+    python tools/kbench.py [--only attention,groupnorm,...] [--reps 20]
+
+Each shape is timed with CUDA events over `reps` back-to-back launches on rotating buffers whose total
+footprint exceeds the 126 MB L2 (so bandwidth kernels see HBM, not L2), after 3 warm-up launches.
+Prints per-shape microseconds and achieved GB/s or TFLOP/s against MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tweediemix_b200 import build, ops  # noqa: E402
+
+B = 4
+DT = torch.bfloat16
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return d["hbm_gbs"], d["bf16_tflops"]
+    except Exception:
+        return 6650.0, 1590.0
+
+
+def timeit(fn, nbuf, reps):
+    for i in range(3):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i % nbuf)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps          # us
+
+
+def nbuf_for(nbytes):
+    return max(2, min(64, int(300e6 // max(nbytes, 1)) + 1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    only = set(args.only.split(",")) if args.only else None
+    build.build()
+    hbm, tf = peaks()
+    dev = "cuda"
+    out = []
+
+    def want(name):
+        return only is None or name in only
+
+    if want("groupnorm"):
+        # (C, HW, count per forward): ResNet norm1/norm2 + Transformer2D norm + conv_norm_out sites
+        sites = [(320, 16384, 5), (640, 16384, 2), (960, 16384, 1), (320, 4096, 1), (640, 4096, 9), (1280, 4096, 1), (1920, 4096, 1), (960, 4096, 1),
+                 (640, 1024, 1), (1280, 1024, 20), (2560, 1024, 2), (1920, 1024, 1)]
+        for C, HW, cnt in sites:
+            h = int(HW ** 0.5)
+            nb = nbuf_for(B * C * HW * 2 * 2)
+            xs = [torch.randn(B, C, h, h, device=dev, dtype=DT).contiguous(memory_format=torch.channels_last) for _ in range(nb)]
+            ys = [torch.empty_like(x) for x in xs]
+            g, b_ = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+            us = timeit(lambda i: ops.group_norm(xs[i], g, b_, 32, 1e-5, silu=True, out=ys[i]), nb, args.reps)
+            nbytes = 2 * B * C * HW * 2
+            out.append(("groupnorm", f"C{C}_HW{HW} x{cnt}", us, nbytes / us / 1e3, "GB/s", hbm))
+    if want("layernorm"):
+        for N, D, cnt in [(4096, 640, 30), (1024, 1280, 180)]:
+            nb = nbuf_for(B * N * D * 4)
+            xs = [torch.randn(B, N, D, device=dev, dtype=DT) for _ in range(nb)]
+            ys = [torch.empty_like(x) for x in xs]
+            g, b_ = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+            us = timeit(lambda i: ops.layer_norm(xs[i], g, b_, 1e-5, out=ys[i]), nb, args.reps)
+            out.append(("layernorm", f"N{N}_D{D} x{cnt}", us, 2 * B * N * D * 2 / us / 1e3, "GB/s", hbm))
+    if want("resadd"):
+        for n, cnt in [(B * 4096 * 640, 40), (B * 1024 * 1280, 190), (B * 16384 * 320, 8)]:
+            nb = nbuf_for(n * 6)
+            a = [torch.randn(n, device=dev, dtype=DT) for _ in range(nb)]
+            b_ = [torch.randn(n, device=dev, dtype=DT) for _ in range(nb)]
+            us = timeit(lambda i: ops.residual_add(a[i], b_[i], out=a[i]), nb, args.reps)
+            out.append(("resadd", f"n{n} x{cnt}", us, 3 * n * 2 / us / 1e3, "GB/s", hbm))
+    if want("geglu"):
+        for N, D, cnt in [(4096, 640, 10), (1024, 1280, 60)]:
+            nb = nbuf_for(B * N * 8 * D * 2 * 1.5)
+            xs = [torch.randn(B, N, 8 * D, device=dev, dtype=DT) for _ in range(nb)]
+            ys = [torch.empty(B, N, 4 * D, device=dev, dtype=DT) for _ in range(nb)]
+            us = timeit(lambda i: ops.geglu(xs[i], out=ys[i]), nb, args.reps)
+            out.append(("geglu", f"N{N}_F{4 * D} x{cnt}", us, 3 * B * N * 4 * D * 2 / us / 1e3, "GB/s", hbm))
+    if want("attention"):
+        for N, Nk, H, cnt in [(4096, 4096, 10, 10), (1024, 1024, 20, 60), (4096, 77, 10, 10), (1024, 77, 20, 60)]:
+            nb = 4
+            if Nk == N:
+                qkv = [torch.randn(B, N, 3 * H * 64, device=dev, dtype=DT) for _ in range(nb)]
+                q = [t[..., :H * 64] for t in qkv]; k = [t[..., H * 64:2 * H * 64] for t in qkv]; v = [t[..., 2 * H * 64:] for t in qkv]
+            else:
+                q = [torch.randn(B, N, H * 64, device=dev, dtype=DT) for _ in range(nb)]
+                kv = [torch.randn(B, Nk, 2 * H * 64, device=dev, dtype=DT) for _ in range(nb)]
+                k = [t[..., :H * 64] for t in kv]; v = [t[..., H * 64:] for t in kv]
+            o = [torch.empty(B, N, H * 64, device=dev, dtype=DT) for _ in range(nb)]
+            us = timeit(lambda i: ops.attention(q[i], k[i], v[i], H, out=o[i]), nb, args.reps)
+            fl = 4.0 * B * H * N * Nk * 64
+            out.append(("attention", f"Nq{N}_Nk{Nk}_H{H} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
+    if want("blend"):
+        for imgs in (1, 2048):
+            x = torch.randn(imgs, 4, 128, 128, device=dev)
+            e = torch.randn(imgs, 4, 4, 128, 128, device=dev, dtype=DT)
+            m = (torch.rand(3, 1, 128, 128, device=dev) > 0.5).float()
+            o = torch.empty_like(x)
+            us = timeit(lambda i: ops.tweedie_blend_ddim(x, e, m, 0.0438, 0.0518, 0.8, out=o), 1, args.reps)
+            nbytes = imgs * (4 * 16384 * 8 + 16 * 16384 * 2) + 3 * 16384 * 4
+            out.append(("blend", f"imgs{imgs}", us, nbytes / us / 1e3, "GB/s", hbm))
+    tot = {}
+    for fam, tag, us, rate, unit, peak in out:
+        print(f"{fam:10s} {tag:28s} {us:9.2f} us  {rate:9.1f} {unit:8s} {100 * rate / peak:5.1f}% of measured peak")
+        cnt = int(tag.split(" x")[1]) if " x" in tag else 0
+        tot[fam] = tot.get(fam, 0.0) + us * cnt
+    print("per fused K=3 step (us, kernels back to back):", {k: round(v, 1) for k, v in tot.items() if v})
+
+
+if __name__ == "__main__":
+    main()

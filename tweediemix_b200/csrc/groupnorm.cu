@@ -45,7 +45,7 @@ __device__ __forceinline__ float silu(float y) { return __fdividef(y, 1.f + __ex
 // grid (P, N); block = CV * RY threads (CV = C/8 channel vectors, RY row lanes).
 // Thread (ty, tx) owns channel vector tx and rows r = row0 + ty, + RY, ...
 template <typename T>
-__global__ void __launch_bounds__(kGnMaxThreads)
+__global__ void __launch_bounds__(kGnMaxThreads, 2)
 gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __restrict__ part,
               float* __restrict__ pivots, int C, int HW, int G, int rows_per_cta) {
     extern __shared__ float2 sh[];                      // [RY][C]
@@ -65,20 +65,23 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
         ad[j] = add ? add[(size_t)n * C + c] : 0.f;
         S[j] = 0.f; SS[j] = 0.f;
     }
+    float kk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) kk[j] = piv[j] - ad[j];
     const T* col = xn + (size_t)tx * 8;
     int r = row0 + ty;
-    for (; r + 3 * RY < row1; r += 4 * RY) {            // 4 independent 128-bit loads in flight
-        float f0[8], f1[8], f2[8], f3[8];
-        V8<T>::load(col + (size_t)r * C, f0, true);
-        V8<T>::load(col + (size_t)(r + RY) * C, f1, true);
-        V8<T>::load(col + (size_t)(r + 2 * RY) * C, f2, true);
-        V8<T>::load(col + (size_t)(r + 3 * RY) * C, f3, true);
+    if constexpr (sizeof(T) == 2) {
+        for (; r + 3 * RY < row1; r += 4 * RY) {        // 4 independent 128-bit loads in flight, unpacked one at a time
+            uint4 q[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float k = piv[j] - ad[j];
-            float d0 = f0[j] - k, d1 = f1[j] - k, d2 = f2[j] - k, d3 = f3[j] - k;
-            S[j] += (d0 + d1) + (d2 + d3);
-            SS[j] = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, SS[j]))));
+            for (int u = 0; u < 4; ++u) q[u] = ld_keep(col + (size_t)(r + u * RY) * C);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8<T>(q[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = f[j] - kk[j]; S[j] += d; SS[j] = fmaf(d, d, SS[j]); }
+            }
         }
     }
     for (; r < row1; r += RY) {
@@ -86,7 +89,7 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
         V8<T>::load(col + (size_t)r * C, f0, true);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float d0 = f0[j] - (piv[j] - ad[j]);
+            const float d0 = f0[j] - kk[j];
             S[j] += d0; SS[j] = fmaf(d0, d0, SS[j]);
         }
     }
@@ -112,7 +115,7 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kGnMaxThreads)
+__global__ void __launch_bounds__(kGnMaxThreads, 2)
 gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ add, const float2* __restrict__ part,
               const float* __restrict__ pivots, T* __restrict__ y,
@@ -145,18 +148,22 @@ gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
     const T* col = xn + (size_t)tx * 8;
     T* ycol = y + (size_t)n * HW * C + (size_t)tx * 8;
     int r = row0 + ty;
-    for (; r + 3 * RY < row1; r += 4 * RY) {
-        float f[4][8];
+    if constexpr (sizeof(T) == 2) {
+        for (; r + 3 * RY < row1; r += 4 * RY) {
+            uint4 q[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) V8<T>::load(col + (size_t)(r + u * RY) * C, f[u], false);
+            for (int u = 0; u < 4; ++u) q[u] = ld_stream(col + (size_t)(r + u * RY) * C);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8<T>(q[u], f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float v = fmaf(f[u][j], a[j], b[j]);
-                f[u][j] = act ? silu(v) : v;
+                for (int j = 0; j < 8; ++j) {
+                    const float v = fmaf(f[j], a[j], b[j]);
+                    f[j] = act ? silu(v) : v;
+                }
+                st_stream(ycol + (size_t)(r + u * RY) * C, pack8<T>(f));
             }
-            V8<T>::store(ycol + (size_t)(r + u * RY) * C, f[u]);
         }
     }
     for (; r < row1; r += RY) {
@@ -246,9 +253,9 @@ static GnPlan plan_nhwc(int N, int C, int HW) {
     p.RY = kGnMaxThreads / CV;
     if (p.RY > HW) p.RY = HW;
     p.threads = CV * p.RY;
-    int want = (4 * sm_count() + N - 1) / N;                 // ~4 CTAs per SM over the whole grid
+    int want = (6 * sm_count() + N - 1) / N;                 // ~6 CTAs per SM over the whole grid (2 resident)
     int rows = (HW + want - 1) / want;
-    const int min_rows = 8 * p.RY;                           // >= 8 rows per thread when possible
+    const int min_rows = 4 * p.RY;                           // >= 4 rows per thread when possible
     if (rows < min_rows) rows = min_rows;
     rows = ((rows + p.RY - 1) / p.RY) * p.RY;
     if (rows > HW) rows = HW;

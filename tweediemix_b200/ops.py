@@ -239,6 +239,20 @@ def residual_add(a, b, inv_scale: float = 1.0, out=None):
     return out
 
 
+def layer_norm(x, gamma, beta, eps: float, out=None):
+    """LayerNorm over the last dim of a contiguous fp16 / bf16 tensor; gamma / beta fp32 [D]."""
+    _dev(x, gamma, beta, out)
+    assert x.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    D = x.shape[-1]
+    rows = x.numel() // D
+    if out is None:
+        out = torch.empty_like(x)
+    with _Launch("layernorm", 1, f"D{D}", 2.0 * x.numel() * x.element_size()):
+        rc = _lib.load().tmx_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(out), rows, D, float(eps), _dt(x), _stream())
+    _lib.check(rc, "tmx_layernorm_fwd")
+    return out
+
+
 def geglu(x, out=None):
     """x [..., 2F] -> x[..., :F] * gelu(x[..., F:]) (exact erf GELU); fp16 / bf16."""
     _dev(x, out)

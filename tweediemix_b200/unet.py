@@ -12,7 +12,7 @@ the execution is laid out for B200:
 
   * activations stay NHWC (``channels_last``) in bf16/fp16 end to end: the ``[B, HW, C]`` token view
     the transformer blocks need is the same memory, so the reference's NCHW<->token permutes vanish;
-  * GroupNorm(+temb add)(+SiLU), the ResNet / transformer residual adds, GEGLU gating and all
+  * GroupNorm(+temb add)(+SiLU), LayerNorm, the ResNet / transformer residual adds, GEGLU gating and all
     attention (self and cross) run in the hand-written sm_100a kernels of ``libtmx.so`` (``ops``);
   * self-attention Q/K/V come from ONE packed projection whose output is consumed in place by the
     attention kernel through strided TMA descriptors (no split / permute / head reshape);
@@ -269,7 +269,10 @@ class BasicTransformerBlock(nn.Module):
 
     @staticmethod
     def _ln(norm: nn.LayerNorm, h):
-        return F.layer_norm(h, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
+        p32 = norm.__dict__.get("_p32")
+        if p32 is None or p32[0].device != norm.weight.device:
+            p32 = norm.__dict__["_p32"] = (norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
+        return ops.layer_norm(h, p32[0], p32[1], norm.eps)
 
     @staticmethod
     def _call_attn(attn: TmxAttention, x, ehs, residual):
@@ -479,6 +482,8 @@ class TmxUNet2DConditionModel(nn.Module):
                 m.drop_packed()
             elif isinstance(m, TmxGroupNorm):
                 m._w32 = m._b32 = None
+            elif isinstance(m, nn.LayerNorm):
+                m.__dict__.pop("_p32", None)
         self._temb_w = self._temb_b = None
         return self
 
