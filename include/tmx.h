@@ -117,7 +117,10 @@ TMX_API int tmx_blend_finish_fwd(const float* x, const float* acc, const float* 
  *
  * x, y      : dtype [N, C, HW] (TMX_NCHW) or [N, HW, C] (TMX_NHWC); y may alias x
  * gamma/beta: fp32 [C];  add: fp32 [N, C] or NULL
- * workspace : tmx_groupnorm_workspace_bytes(N, C, HW, G, layout) bytes, 16-byte aligned
+ * workspace : tmx_groupnorm_workspace_bytes(N, C, HW, G, layout) bytes, 16-byte aligned; its first 4 KiB
+ *             (per-row completion tickets) must be ZERO before the first launch — the kernels leave
+ *             them zero again, so one memset at allocation is enough; N <= 1024;
+ *             one launch at a time per workspace (launches on the same stream are fine)
  * Statistics in fp32 (Chan/Welford merge, deterministic), one rounding on store.
  * Requires C % G == 0, C % 8 == 0 (NHWC) or HW*(C/G) % 8 == 0 (NCHW).
  * Algorithmic bytes: 2 * N*C*HW * sizeof(dtype).

@@ -31,13 +31,24 @@ def peaks():
 
 
 def timeit(fn, nbuf, reps):
+    """Device time per launch: the `reps` launches are captured in ONE CUDA graph (as the sampler replays
+    them), so the Python / ctypes launch cost (~10 us per call in eager mode) is not what is measured."""
     for i in range(3):
         fn(i % nbuf)
     torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for i in range(reps):
+                fn(i % nbuf)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(reps):
-        fn(i % nbuf)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps          # us

@@ -26,6 +26,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags():
+    """NVCC_FLAGS plus optional tuning defines from $TMX_NVCC_EXTRA (e.g. "-DTMX_ATTN_POLY_EVERY=4")."""
+    return NVCC_FLAGS + os.environ.get("TMX_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -45,7 +50,7 @@ def _digest() -> str:
         h.update(p.encode())
         with open(p, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -58,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [_nvcc(), *_flags(), "-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

@@ -6,14 +6,24 @@
 //   * S = Q K^T and O += P V are tcgen05.mma (kind::f16, M=128) issued by ONE elected thread,
 //     accumulators live in TMEM; P is written back to TMEM as packed 16-bit and consumed as the
 //     A operand of the second MMA (TS form), so P never touches shared memory;
-//   * warp-specialised: warp 0 = TMA producer (+ TMEM alloc), warp 1 = MMA issuer, then one
-//     128-thread softmax group per 128-row query tile (thread == row == TMEM lane), all linked by
-//     mbarriers; tcgen05.commit signals MMA completion;
+//   * warp-specialised: warp 0 = TMA producer (+ TMEM alloc), one MMA-issuer warp PER query tile
+//     (each blocks only on its own tile's barriers, so a tile that is ahead is never queued behind
+//     the other one), then one 128-thread softmax group per 128-row query tile (thread == row ==
+//     TMEM lane), all linked by mbarriers; tcgen05.commit signals MMA completion;
 //   * online softmax in the exp2 domain with lazy rescaling of O (only when the running max
 //     moves by more than 2^8), exact because the row sum is accumulated against the same
-//     reference.
+//     reference;
+//   * the S buffer of a query tile is released (s_free) as soon as its 128 columns sit in
+//     registers, so the tensor pipe computes S(j+1) = Q K(j+1)^T WHILE the softmax of tile j runs;
+//     P has its own TMEM columns and is guarded by pv_done (tcgen05.commit after P V);
+//   * head dim 64 makes the kernel exp-bound, not MMA-bound: 16 MUFU.EX2 / clk / SM against 8192
+//     tensor FLOP / clk / SM is 1024 vs 512 clk per 128x128 tile (ex2.approx.f16x2 is no way out: it
+//     lowers to two MUFU.EX2.F16, checked in SASS).  kPolyEvery > 0 moves one exponential in every
+//     kPolyEvery pairs to the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error
+//     7.5e-5 << the 2^-9 rounding of P); measured neutral on B200 because the softmax warps are then
+//     issue-bound, so the default is all-MUFU.
 // NQ = query tiles per CTA.  NQ=1: 192 threads, 256 TMEM columns, two CTAs per SM overlap each
-// other's softmax and MMA phases.  NQ=2: 320 threads, 512 TMEM columns, the two tiles ping-pong on
+// other's softmax and MMA phases.  NQ=2: 384 threads, 512 TMEM columns, the two tiles ping-pong on
 // the tensor pipe and share every K/V tile (half the L2->SMEM traffic).
 //
 // Replaces the einsum -> softmax -> einsum of fusion_generation/utils_custom.py:91-105 and
@@ -28,6 +38,10 @@ constexpr int kBM = 128;             // query rows per tile  (UMMA M)
 constexpr int kBN = 128;             // kv rows per tile     (UMMA N of QK^T, K of PV)
 constexpr int kTileBytes = kBM * kD * 2;         // 16 KiB, one 128x64 16-bit tile
 constexpr float kRescaleThreshold = 8.0f;        // log2 domain
+#ifndef TMX_ATTN_POLY_EVERY
+#define TMX_ATTN_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = TMX_ATTN_POLY_EVERY;  // of every kPolyEvery PAIRS of exponentials one goes to the FMA pipe (0 = all MUFU): 2 -> 25 %
 
 __device__ unsigned int g_attn_timeout_flag = 0;
 
@@ -135,6 +149,19 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+// 2^x on the FMA/ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5), 2^n by adding n to the exponent field.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.f);
+    const float magic = 12582912.f;                      // 1.5 * 2^23: low mantissa bits of (x + magic) hold round(x)
+    const float xr = x + magic;
+    const float f = x - (xr - magic);
+    float p = fmaf(f, 0.05517132208f, 0.24261054397f);   // minimax of 2^f on [-0.5, 0.5], max rel. error 7.5e-5
+    p = fmaf(p, f, 0.69326096773f);
+    p = fmaf(p, f, 0.99992811680f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+
 // ------------------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) |
 // SBO>>4 [32,46) | version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
@@ -148,10 +175,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, fp32 accumulate.
-__host__ __device__ constexpr uint32_t make_idesc(bool bf16, int M, int N, bool b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(bool a_bf16, bool b_bf16, int M, int N, bool b_mn_major) {
     return (1u << 4)                              // c_format = F32
-         | ((bf16 ? 1u : 0u) << 7)                // a_format
-         | ((bf16 ? 1u : 0u) << 10)               // b_format
+         | ((a_bf16 ? 1u : 0u) << 7)              // a_format (0 = F16, 1 = BF16)
+         | ((b_bf16 ? 1u : 0u) << 10)             // b_format
          | (0u << 15)                             // a_major = K
          | ((b_mn_major ? 1u : 0u) << 16)         // b_major
          | ((uint32_t)(N >> 3) << 17)             // n_dim
@@ -172,9 +199,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // ------------------------------------------------------------------------------------- kernel
 template <int NQ> struct AttnCfg {
     static constexpr int kStages = NQ == 1 ? 2 : 3;
-    static constexpr int kThreads = 64 + 128 * NQ;
+    static constexpr int kFirstSoftmaxWarp = NQ == 1 ? 2 : 4;      // warps: 0 TMA, 1..NQ MMA issuers, (pad), softmax groups
+    static constexpr int kThreads = 32 * kFirstSoftmaxWarp + 128 * NQ;
     static constexpr int kTmemCols = 256 * NQ;                     // per tile: S[0,128) O[128,192) P[192,256)
-    static constexpr int kBars = 3 * NQ + NQ + 4 * kStages;        // s_full,p_full,o_full,q_full + k/v full/empty
+    static constexpr int kBars = 5 * NQ + 4 * kStages;             // q_full,s_full,s_free,p_full,pv_done + k/v full/empty
     static constexpr int kSmemBytes = 1024 /*align slack*/ + (NQ + 2 * kStages) * kTileBytes + kBars * 8 + 16;
 };
 
@@ -191,11 +219,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t* sK = sQ + NQ * kTileBytes;
     uint8_t* sV = sK + ST * kTileBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * kTileBytes);
-    uint64_t* q_full = bars;                   // [NQ]
-    uint64_t* s_full = q_full + NQ;            // [NQ]
-    uint64_t* p_full = s_full + NQ;            // [NQ]
-    uint64_t* o_full = p_full + NQ;            // [NQ]
-    uint64_t* k_full = o_full + NQ;            // [ST]
+    uint64_t* q_full = bars;                   // [NQ]  TMA -> MMA       : Q tile landed
+    uint64_t* s_full = q_full + NQ;            // [NQ]  MMA -> softmax   : S(j) = Q K(j)^T complete
+    uint64_t* s_free = s_full + NQ;            // [NQ]  softmax -> MMA   : S(j) copied to registers, buffer reusable
+    uint64_t* p_full = s_free + NQ;            // [NQ]  softmax -> MMA   : P(j) written to TMEM
+    uint64_t* pv_done = p_full + NQ;           // [NQ]  MMA -> softmax   : O += P(j) V(j) complete (P buffer / O readable)
+    uint64_t* k_full = pv_done + NQ;           // [ST]
     uint64_t* k_empty = k_full + ST;
     uint64_t* v_full = k_empty + ST;
     uint64_t* v_empty = v_full + ST;
@@ -206,8 +235,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int T = (Nk + kBN - 1) / kBN;
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
-        for (int i = 0; i < ST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        for (int i = 0; i < NQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+        for (int i = 0; i < ST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], NQ); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], NQ); }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -238,56 +267,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tma_load_4d(sV + st * kTileBytes, &tm_v, &v_full[st], 0, h, j * kBN, b);
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
+    } else if (warp <= NQ) {
+        // ================================ MMA issuer of query tile w ===================
         if (lane == 0) {
-            constexpr uint32_t idesc_qk = make_idesc(BF16, kBM, kBN, false);
-            constexpr uint32_t idesc_pv = make_idesc(BF16, kBM, kD, true);
-            auto issue_qk = [&](int w, int st) {
-                const uint32_t a0 = smem_u32(sQ + w * kTileBytes), b0 = smem_u32(sK + st * kTileBytes);
+            const int w = warp - 1;
+            constexpr uint32_t idesc_qk = make_idesc(BF16, BF16, kBM, kBN, false);
+            constexpr uint32_t idesc_pv = make_idesc(BF16, BF16, kBM, kD, true);
+            const uint32_t t_s = tmem_base + w * 256, t_o = t_s + 128, t_p = t_s + 192;
+            const uint32_t a0 = smem_u32(sQ + w * kTileBytes);
+            auto issue_qk = [&](int st) {
+                const uint32_t b0 = smem_u32(sK + st * kTileBytes);
 #pragma unroll
                 for (int k = 0; k < kD / 16; ++k)                    // 4 x (K = 16): +32 B inside the 128 B swizzle row
-                    umma_ss(tmem_base + w * 256, make_sw128_desc(a0 + k * 32, 16, 1024),
-                            make_sw128_desc(b0 + k * 32, 16, 1024), idesc_qk, k > 0);
+                    umma_ss(t_s, make_sw128_desc(a0 + k * 32, 16, 1024), make_sw128_desc(b0 + k * 32, 16, 1024), idesc_qk, k > 0);
             };
-            auto issue_pv = [&](int w, int st, bool acc) {
+            auto issue_pv = [&](int st, bool acc) {
                 const uint32_t b0 = smem_u32(sV + st * kTileBytes);
 #pragma unroll
                 for (int k = 0; k < kBN / 16; ++k)                   // 8 x (K = 16 kv rows): +2048 B in V, +8 columns in P
-                    umma_ts(tmem_base + w * 256 + 128, tmem_base + w * 256 + 192 + k * 8,
-                            make_sw128_desc(b0 + k * 2048, 16, 1024), idesc_pv, (acc || k > 0) ? 1u : 0u);
+                    umma_ts(t_o, t_p + k * 8, make_sw128_desc(b0 + k * 2048, 16, 1024), idesc_pv, (acc || k > 0) ? 1u : 0u);
             };
             mbar_wait(&k_full[0], 0);
-            for (int w = 0; w < NQ; ++w) {
-                mbar_wait(&q_full[w], 0);
-                tc_fence_after();
-                issue_qk(w, 0);
-                umma_commit(&s_full[w]);
-            }
+            mbar_wait(&q_full[w], 0);
+            tc_fence_after();
+            issue_qk(0);
+            umma_commit(&s_full[w]);
             umma_commit(&k_empty[0]);
             for (int j = 0; j < T; ++j) {
                 const int st = j % ST, stn = (j + 1) % ST;
                 const uint32_t ph = (uint32_t)(j / ST) & 1u, phn = (uint32_t)((j + 1) / ST) & 1u;
-                for (int w = 0; w < NQ; ++w) {
-                    mbar_wait(&p_full[w], (uint32_t)j & 1u);
-                    if (w == 0) mbar_wait(&v_full[st], ph);
+                if (j + 1 < T) {
+                    // S(j+1) as soon as the softmax group holds S(j) in registers: overlaps its exp phase
+                    mbar_wait(&k_full[stn], phn);
+                    mbar_wait(&s_free[w], (uint32_t)j & 1u);
                     tc_fence_after();
-                    issue_pv(w, st, j > 0);
-                    if (w == NQ - 1) umma_commit(&v_empty[st]);
-                    if (j + 1 < T) {
-                        if (w == 0) { mbar_wait(&k_full[stn], phn); tc_fence_after(); }
-                        issue_qk(w, stn);
-                        umma_commit(&s_full[w]);
-                        if (w == NQ - 1) umma_commit(&k_empty[stn]);
-                    } else {
-                        umma_commit(&o_full[w]);
-                    }
+                    issue_qk(stn);
+                    umma_commit(&s_full[w]);
+                    umma_commit(&k_empty[stn]);
                 }
+                mbar_wait(&v_full[st], ph);
+                mbar_wait(&p_full[w], (uint32_t)j & 1u);
+                tc_fence_after();
+                issue_pv(st, j > 0);
+                umma_commit(&pv_done[w]);
+                umma_commit(&v_empty[st]);
             }
         }
-    } else {
+    } else if (warp >= Cfg::kFirstSoftmaxWarp) {
         // ================================ softmax / correction / epilogue ==============
-        const int w = (warp - 2) >> 2;                       // query tile handled by this warp group
+        const int w = (warp - Cfg::kFirstSoftmaxWarp) >> 2;  // query tile handled by this warp group
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;                 // row in the tile == TMEM lane
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + w * 256;
@@ -303,6 +331,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
             tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
             tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&s_free[w]);                                   // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
             const int valid = Nk - j * kBN;
             if (valid < kBN) {
 #pragma unroll
@@ -318,7 +348,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             // lazy rescale: move the reference only when the max grew by more than 2^8
             const bool bump = m_tile > m_ref + kRescaleThreshold;
             const float m_new = bump ? m_tile : m_ref;
+            bool pv_waited = false;
             if (j > 0 && __any_sync(0xffffffffu, bump)) {            // warp-uniform: tcgen05.ld/st are warp-collective
+                mbar_wait(&pv_done[w], (uint32_t)(j - 1) & 1u);      // O must hold every P V issued so far
+                tc_fence_after();
+                pv_waited = true;
                 const float alpha = bump ? ex2(m_ref - m_new) : 1.f;
                 l_sum *= alpha;
 #pragma unroll
@@ -338,10 +372,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 uint32_t p[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    const float e0 = ex2(fmaf(__uint_as_float(s[q * 32 + 2 * c]), scale_log2, -m_new));
-                    const float e1 = ex2(fmaf(__uint_as_float(s[q * 32 + 2 * c + 1]), scale_log2, -m_new));
+                    const float x0 = fmaf(__uint_as_float(s[q * 32 + 2 * c]), scale_log2, -m_new);
+                    const float x1 = fmaf(__uint_as_float(s[q * 32 + 2 * c + 1]), scale_log2, -m_new);
+                    const float e0 = ex2(x0);
+                    const float e1 = (kPolyEvery > 0 && (c % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(x1) : ex2(x1);
                     sum0 += e0; sum1 += e1;
                     p[c] = pack2<BF16>(e0, e1);
+                }
+                if (q == 0 && j > 0 && !pv_waited) {                   // P(j-1) must have been consumed before it is overwritten
+                    mbar_wait(&pv_done[w], (uint32_t)(j - 1) & 1u);
+                    tc_fence_after();
                 }
                 tmem_st16(t_row + 192 + q * 16, p);
             }
@@ -352,7 +392,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
 
         // epilogue: O / l -> global (row-contiguous 128 B per thread)
-        mbar_wait(&o_full[w], 0);
+        mbar_wait(&pv_done[w], (uint32_t)(T - 1) & 1u);
         tc_fence_after();
         const float inv_l = 1.f / l_sum;
         const int q_row = q0 + w * kBM + row;

@@ -43,7 +43,8 @@ __device__ __forceinline__ void store8_f32(float* p, const float (&f)[8]) {
     st_stream(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
 }
 
-// One thread: one image, 8 consecutive pixels, all C channels.
+// One thread: one image, one channel, 8 consecutive pixels (a single round of independent loads:
+// at one image the kernel is pure latency, so nothing may be serialised behind a channel loop).
 template <typename T, bool REF>
 __global__ void __launch_bounds__(256)
 blend_kernel(const float* __restrict__ x, const T* __restrict__ eps, const float* __restrict__ masks,
@@ -51,15 +52,16 @@ blend_kernel(const float* __restrict__ x, const T* __restrict__ eps, const float
              int imgs, int K, int C, int HW, const __grid_constant__ BlendCoef cf) {
     const int groups = HW >> 3;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)imgs * groups) return;
-    const int img = (int)(idx / groups);
-    const int p = (int)(idx - (long long)img * groups) << 3;
+    if (idx >= (long long)imgs * C * groups) return;
+    const int p = (int)(idx % groups) << 3;
+    const int ch = (int)((idx / groups) % C);
+    const int img = (int)(idx / ((long long)groups * C));
 
     const size_t chw = (size_t)C * HW;
     const float* xi = x + (size_t)img * chw + p;
     const T* ei = eps + (size_t)img * (K + 1) * chw + p;
 
-    for (int ch = 0; ch < C; ++ch) {
+    {
         float xv[8], eu[8], acc[8];
         Vec8<float>::load(xi + (size_t)ch * HW, xv);
         Vec8<T>::load(ei + (size_t)ch * HW, eu);
@@ -214,7 +216,7 @@ static BlendCoef make_coef(float a_t, float a_next, float g, int is_last, const 
 template <typename T>
 static int launch_blend(const float* x, const void* eps, const float* masks, float* x_out, float* x0_out,
                         int imgs, int K, int C, int HW, const BlendCoef& cf, int round_mode, cudaStream_t st) {
-    const long long total = (long long)imgs * (HW >> 3);
+    const long long total = (long long)imgs * C * (HW >> 3);
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     if (round_mode == TMX_ROUND_REF)

@@ -7,7 +7,20 @@
 
 namespace tmx {
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+// exact-GELU  0.5 v (1 + erf(v / sqrt 2))  with erf from Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far
+// below the 2^-9 / 2^-12 output rounding): one MUFU.RCP + one MUFU.EX2 + 7 FMAs instead of libdevice erff's
+// ~25-instruction branchy path, which made this kernel issue-bound instead of HBM-bound.
+__device__ __forceinline__ float gelu_erf(float v) {
+    const float z = fabsf(v) * 0.70710678118654752f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = p * t * exp2f(-1.4426950408889634f * z * z);     // 1 - erf(z), z >= 0
+    const float half_erfc = 0.5f * e;                                 // Phi(-|v|)
+    return v >= 0.f ? v * (1.f - half_erfc) : v * half_erfc;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)

@@ -42,45 +42,69 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 __device__ __forceinline__ float silu(float y) { return __fdividef(y, 1.f + __expf(-y)); }
 
 // ------------------------------------------------------------------------------------------ NHWC
-// grid (P, N); block = CV * RY threads (CV = C/8 channel vectors, RY row lanes).
+// grid (P, N); block = CV * RY threads (CV = C/8 channel vectors, RY row lanes), 2 CTAs per SM.
 // Thread (ty, tx) owns channel vector tx and rows r = row0 + ty, + RY, ...
+//
+// stats: per-CTA shifted partial sums -> part[(n*G+g)*P + p]; the LAST CTA of a row n to finish
+// (ticket counter in the workspace) folds the P partials of every group in a fixed order and
+// publishes stat[n*G+g] = (mean, rstd), so `apply` starts with two floats per group instead of
+// re-reducing the partials in every CTA.
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads, 2)
 gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __restrict__ part,
-              float* __restrict__ pivots, int C, int HW, int G, int rows_per_cta) {
-    extern __shared__ float2 sh[];                      // [RY][C]
+              float2* __restrict__ stat, unsigned int* __restrict__ tickets,
+              int C, int HW, int G, int rows_per_cta, float eps) {
+    extern __shared__ float2 sh[];                      // [RY][C] partials, then reused
+    __shared__ float s_piv[64];
+    __shared__ unsigned int s_ticket;
     const int CV = C >> 3, RY = blockDim.x / CV, cpg = C / G;
     const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
     const int n = blockIdx.y, P = gridDim.x;
     const int row0 = blockIdx.x * rows_per_cta;
     const int row1 = min(HW, row0 + rows_per_cta);
     const T* xn = x + (size_t)n * HW * C;
+    const T* col = xn + (size_t)tx * 8;
 
-    float piv[8], ad[8], S[8], SS[8];
+    // first batch of row loads goes out before anything else (the pivot staging below overlaps it)
+    int r = row0 + ty;
+    uint4 q[4];
+    const bool full0 = (sizeof(T) == 2) && (r + 3 * RY < row1);
+    if (full0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = ld_keep(col + (size_t)(r + u * RY) * C);
+    }
+    // pivot = x'[n, pixel 0, first channel of the group]: sums of (x' - pivot) do not cancel
+    for (int g = threadIdx.x; g < G; g += blockDim.x)
+        s_piv[g] = to_f32<T>(xn[g * cpg]) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
+    __syncthreads();
+    float kk[8], S[8], SS[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = tx * 8 + j, g = c / cpg;
-        const float a0 = add ? add[(size_t)n * C + g * cpg] : 0.f;
-        piv[j] = to_f32<T>(xn[g * cpg]) + a0;           // pivot = x'[n, pixel 0, first channel of group]
-        ad[j] = add ? add[(size_t)n * C + c] : 0.f;
+        const int c = tx * 8 + j;
+        kk[j] = s_piv[c / cpg] - (add ? add[(size_t)n * C + c] : 0.f);
         S[j] = 0.f; SS[j] = 0.f;
     }
-    float kk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) kk[j] = piv[j] - ad[j];
-    const T* col = xn + (size_t)tx * 8;
-    int r = row0 + ty;
     if constexpr (sizeof(T) == 2) {
-        for (; r + 3 * RY < row1; r += 4 * RY) {        // 4 independent 128-bit loads in flight, unpacked one at a time
-            uint4 q[4];
+        if (full0) {
+            while (true) {
+                const int rn = r + 4 * RY;
+                const bool more = rn + 3 * RY < row1;
+                uint4 qn[4];
+                if (more) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) q[u] = ld_keep(col + (size_t)(r + u * RY) * C);
+                    for (int u = 0; u < 4; ++u) qn[u] = ld_keep(col + (size_t)(rn + u * RY) * C);
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float f[8];
-                unpack8<T>(q[u], f);
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8<T>(q[u], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const float d = f[j] - kk[j]; S[j] += d; SS[j] = fmaf(d, d, SS[j]); }
+                    for (int j = 0; j < 8; ++j) { const float d = f[j] - kk[j]; S[j] += d; SS[j] = fmaf(d, d, SS[j]); }
+                }
+                r = rn;
+                if (!more) break;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = qn[u];
             }
         }
     }
@@ -88,10 +112,7 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
         float f0[8];
         V8<T>::load(col + (size_t)r * C, f0, true);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float d0 = f0[j] - kk[j];
-            S[j] += d0; SS[j] = fmaf(d0, d0, SS[j]);
-        }
+        for (int j = 0; j < 8; ++j) { const float d0 = f0[j] - kk[j]; S[j] += d0; SS[j] = fmaf(d0, d0, SS[j]); }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) sh[(size_t)ty * C + tx * 8 + j] = make_float2(S[j], SS[j]);
@@ -105,64 +126,83 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
             s += v.x; ss += v.y;
         }
         s = warp_sum(s); ss = warp_sum(ss);
+        if (lane == 0) part[((size_t)n * G + g) * P + blockIdx.x] = make_float2(s, ss);
+    }
+    // ---- last CTA of this row finalises the statistics
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[n], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(P - 1)) return;
+    __threadfence();
+    const float inv = 1.f / ((float)HW * (float)cpg);
+    for (int g = warp; g < G; g += nwarps) {
+        float s = 0.f, ss = 0.f;
+        const float2* pp = part + ((size_t)n * G + g) * P;
+        for (int i = lane; i < P; i += 32) { const float2 v = __ldcg(pp + i); s += v.x; ss += v.y; }
+        s = warp_sum(s); ss = warp_sum(ss);
         if (lane == 0) {
-            part[((size_t)n * G + g) * P + blockIdx.x] = make_float2(s, ss);
-            // the pivot is published once so that `apply` never re-reads x[0] (y may alias x)
-            if (blockIdx.x == 0)
-                pivots[n * G + g] = to_f32<T>(xn[g * cpg]) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
+            const float md = s * inv;
+            const float var = fmaxf(ss * inv - md * md, 0.f);
+            stat[n * G + g] = make_float2(s_piv[g] + md, rsqrtf(var + eps));
         }
     }
+    if (threadIdx.x == 0) tickets[n] = 0u;              // leave the workspace ready for the next launch
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads, 2)
 gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              const float* __restrict__ add, const float2* __restrict__ part,
-              const float* __restrict__ pivots, T* __restrict__ y,
-              int C, int HW, int G, int rows_per_cta, int P_stats, float eps, int act) {
-    __shared__ float s_mean[64], s_rstd[64];
+              const float* __restrict__ add, const float2* __restrict__ stat, T* __restrict__ y,
+              int C, int HW, int G, int rows_per_cta, int act) {
     const int CV = C >> 3, RY = blockDim.x / CV, cpg = C / G;
     const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
     const int n = blockIdx.y;
     const T* xn = x + (size_t)n * HW * C;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        float s = 0.f, ss = 0.f;
-        const float2* pp = part + ((size_t)n * G + g) * P_stats;
-        for (int i = 0; i < P_stats; ++i) { s += pp[i].x; ss += pp[i].y; }
-        const float inv = 1.f / ((float)HW * (float)cpg);
-        const float md = s * inv;
-        const float var = fmaxf(ss * inv - md * md, 0.f);
-        s_mean[g] = pivots[n * G + g] + md;
-        s_rstd[g] = rsqrtf(var + eps);
-    }
-    __syncthreads();
-    float a[8], b[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = tx * 8 + j, g = c / cpg;
-        a[j] = s_rstd[g] * gamma[c];
-        const float adj = add ? add[(size_t)n * C + c] : 0.f;
-        b[j] = fmaf(adj - s_mean[g], a[j], beta[c]);
-    }
     const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
     const T* col = xn + (size_t)tx * 8;
     T* ycol = y + (size_t)n * HW * C + (size_t)tx * 8;
     int r = row0 + ty;
+    uint4 q[4];
+    const bool full0 = (sizeof(T) == 2) && (r + 3 * RY < row1);
+    if (full0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = ld_stream(col + (size_t)(r + u * RY) * C);
+    }
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = tx * 8 + j;
+        const float2 st = __ldcg(stat + n * G + c / cpg);
+        a[j] = st.y * gamma[c];
+        const float adj = add ? add[(size_t)n * C + c] : 0.f;
+        b[j] = fmaf(adj - st.x, a[j], beta[c]);
+    }
     if constexpr (sizeof(T) == 2) {
-        for (; r + 3 * RY < row1; r += 4 * RY) {
-            uint4 q[4];
+        if (full0) {
+            while (true) {
+                const int rn = r + 4 * RY;
+                const bool more = rn + 3 * RY < row1;
+                uint4 qn[4];
+                if (more) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) q[u] = ld_stream(col + (size_t)(r + u * RY) * C);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float f[8];
-                unpack8<T>(q[u], f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float v = fmaf(f[j], a[j], b[j]);
-                    f[j] = act ? silu(v) : v;
+                    for (int u = 0; u < 4; ++u) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * C);
                 }
-                st_stream(ycol + (size_t)(r + u * RY) * C, pack8<T>(f));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8<T>(q[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float v = fmaf(f[j], a[j], b[j]);
+                        f[j] = act ? silu(v) : v;
+                    }
+                    st_stream(ycol + (size_t)(r + u * RY) * C, pack8<T>(f));
+                }
+                r = rn;
+                if (!more) break;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = qn[u];
             }
         }
     }
@@ -253,9 +293,10 @@ static GnPlan plan_nhwc(int N, int C, int HW) {
     p.RY = kGnMaxThreads / CV;
     if (p.RY > HW) p.RY = HW;
     p.threads = CV * p.RY;
-    int want = (6 * sm_count() + N - 1) / N;                 // ~6 CTAs per SM over the whole grid (2 resident)
+    int want = (2 * sm_count() + N - 1) / N;                 // one resident wave: 2 CTAs per SM over the whole grid
+    if (want < 1) want = 1;
     int rows = (HW + want - 1) / want;
-    const int min_rows = 4 * p.RY;                           // >= 4 rows per thread when possible
+    const int min_rows = 8 * p.RY;                           // >= 8 rows per thread when possible (two pipelined batches)
     if (rows < min_rows) rows = min_rows;
     rows = ((rows + p.RY - 1) / p.RY) * p.RY;
     if (rows > HW) rows = HW;
@@ -265,19 +306,24 @@ static GnPlan plan_nhwc(int N, int C, int HW) {
     return p;
 }
 
+// workspace layout: [tickets: 1024 x u32][stat: N*G x float2][pivots (NCHW path): N*G x f32][part: N*G*kGnMaxParts x float2]
+constexpr size_t kGnTicketBytes = 1024 * sizeof(unsigned int);
+static size_t gn_align(size_t v) { return (v + 15) & ~(size_t)15; }
+
 template <typename T>
 static int run_gn(const void* x, const float* gamma, const float* beta, const float* add, void* y, void* ws,
                   int N, int C, int HW, int G, float eps, int act, int layout, cudaStream_t st) {
-    float* pivots = (float*)ws;                                // [N*G], padded to 16 B
-    float2* part = (float2*)((char*)ws + (((size_t)N * G * sizeof(float) + 15) & ~(size_t)15));
+    unsigned int* tickets = (unsigned int*)ws;
+    float2* stat = (float2*)((char*)ws + kGnTicketBytes);
+    float* pivots = (float*)((char*)stat + gn_align((size_t)N * G * sizeof(float2)));
+    float2* part = (float2*)((char*)pivots + gn_align((size_t)N * G * sizeof(float)));
     if (layout == TMX_NHWC) {
         GnPlan p = plan_nhwc(N, C, HW);
         dim3 grid(p.P, N);
         size_t smem = (size_t)p.RY * C * sizeof(float2);
-        gn_stats_nhwc<T><<<grid, p.threads, smem, st>>>((const T*)x, add, part, pivots, C, HW, G, p.rows_per_cta);
+        gn_stats_nhwc<T><<<grid, p.threads, smem, st>>>((const T*)x, add, part, stat, tickets, C, HW, G, p.rows_per_cta, eps);
         TMX_CUDA(cudaGetLastError());
-        gn_apply_nhwc<T><<<grid, p.threads, 0, st>>>((const T*)x, gamma, beta, add, part, pivots, (T*)y, C, HW, G,
-                                                    p.rows_per_cta, p.P, eps, act);
+        gn_apply_nhwc<T><<<grid, p.threads, 0, st>>>((const T*)x, gamma, beta, add, stat, (T*)y, C, HW, G, p.rows_per_cta, act);
         return check_cuda(cudaGetLastError(), "gn_apply_nhwc launch");
     }
     const int cpg = C / G, nvec = cpg * HW / 8;
@@ -304,7 +350,8 @@ using namespace tmx;
 extern "C" size_t tmx_groupnorm_workspace_bytes(int N, int C, int HW, int G, int layout) {
     (void)C; (void)HW; (void)layout;
     if (N <= 0 || G <= 0) return 0;
-    return (((size_t)N * G * sizeof(float) + 15) & ~(size_t)15) + (size_t)N * G * kGnMaxParts * sizeof(float2);
+    return kGnTicketBytes + gn_align((size_t)N * G * sizeof(float2)) + gn_align((size_t)N * G * sizeof(float))
+         + (size_t)N * G * kGnMaxParts * sizeof(float2);
 }
 
 extern "C" int tmx_groupnorm_fwd(const void* x, const float* gamma, const float* beta, const float* add,
@@ -312,6 +359,7 @@ extern "C" int tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
                                  int act, int layout, int dtype, void* stream) {
     TMX_REQUIRE(x && gamma && beta && y && workspace, TMX_EINVAL, "groupnorm: null pointer");
     TMX_REQUIRE(N > 0 && C > 0 && HW > 0 && G > 0, TMX_EINVAL, "groupnorm: non-positive size");
+    TMX_REQUIRE(N <= 1024, TMX_ESHAPE, "groupnorm: N=%d exceeds 1024 rows per launch", N);
     TMX_REQUIRE(G <= 64 && C % G == 0, TMX_ESHAPE, "groupnorm: C=%d not divisible by G=%d (G<=64)", C, G);
     TMX_REQUIRE(act == TMX_ACT_NONE || act == TMX_ACT_SILU, TMX_EINVAL, "groupnorm: bad act %d", act);
     TMX_REQUIRE(aligned16(x) && aligned16(y) && aligned16(workspace), TMX_EALIGN, "groupnorm: 16-byte alignment");

@@ -193,7 +193,7 @@ def _workspace(dev: int, nbytes: int) -> torch.Tensor:
     if ws is None or ws.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("tmx: GroupNorm workspace would have to grow during CUDA-graph capture; run the op once eagerly first")
-        ws = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=f"cuda:{dev}")
+        ws = torch.zeros(max(nbytes, 32 << 20), dtype=torch.uint8, device=f"cuda:{dev}")   # tickets must start at zero
         _gn_ws[dev] = ws
     return ws
 
