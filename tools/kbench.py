@@ -62,6 +62,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--shapes", default="", help="comma-separated substrings; only shapes whose tag contains one are run (profiling aid)")
     args = ap.parse_args()
     only = set(args.only.split(",")) if args.only else None
     build.build()
@@ -72,11 +73,18 @@ def main():
     def want(name):
         return only is None or name in only
 
+    shapes = [t for t in args.shapes.split(",") if t]
+
+    def keep(tag):
+        return not shapes or any(t in tag for t in shapes)
+
     if want("groupnorm"):
         # (C, HW, count per forward): ResNet norm1/norm2 + Transformer2D norm + conv_norm_out sites
         sites = [(320, 16384, 5), (640, 16384, 2), (960, 16384, 1), (320, 4096, 1), (640, 4096, 9), (1280, 4096, 1), (1920, 4096, 1), (960, 4096, 1),
                  (640, 1024, 1), (1280, 1024, 20), (2560, 1024, 2), (1920, 1024, 1)]
         for C, HW, cnt in sites:
+            if not keep(f"C{C}_HW{HW}"):
+                continue
             h = int(HW ** 0.5)
             nb = nbuf_for(B * C * HW * 2 * 2)
             xs = [torch.randn(B, C, h, h, device=dev, dtype=DT).contiguous(memory_format=torch.channels_last) for _ in range(nb)]
@@ -87,6 +95,8 @@ def main():
             out.append(("groupnorm", f"C{C}_HW{HW} x{cnt}", us, nbytes / us / 1e3, "GB/s", hbm))
     if want("layernorm"):
         for N, D, cnt in [(4096, 640, 30), (1024, 1280, 180)]:
+            if not keep(f"N{N}_D{D}"):
+                continue
             nb = nbuf_for(B * N * D * 4)
             xs = [torch.randn(B, N, D, device=dev, dtype=DT) for _ in range(nb)]
             ys = [torch.empty_like(x) for x in xs]
@@ -109,6 +119,8 @@ def main():
             out.append(("geglu", f"N{N}_F{4 * D} x{cnt}", us, 3 * B * N * 4 * D * 2 / us / 1e3, "GB/s", hbm))
     if want("attention"):
         for N, Nk, H, cnt in [(4096, 4096, 10, 10), (1024, 1024, 20, 60), (4096, 77, 10, 10), (1024, 77, 20, 60)]:
+            if not keep(f"Nq{N}_Nk{Nk}_H{H}"):
+                continue
             nb = 4
             if Nk == N:
                 qkv = [torch.randn(B, N, 3 * H * 64, device=dev, dtype=DT) for _ in range(nb)]
@@ -123,6 +135,8 @@ def main():
             out.append(("attention", f"Nq{N}_Nk{Nk}_H{H} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
     if want("blend"):
         for imgs in (1, 2048):
+            if not keep(f"imgs{imgs}"):
+                continue
             x = torch.randn(imgs, 4, 128, 128, device=dev)
             e = torch.randn(imgs, 4, 4, 128, 128, device=dev, dtype=DT)
             m = (torch.rand(3, 1, 128, 128, device=dev) > 0.5).float()
