@@ -306,7 +306,7 @@ def run_ours(args):
                     "launches": n, "avg_launch_ms": ms / n, "flops_per_launch": work / n,
                     "by_shape": {tag: {"launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
                                        "tflops": d["work"] / (d["ms"] * 1e-3) / 1e12} for tag, d in fam["attention"]}}
-    for f in ("groupnorm", "resadd", "geglu", "blend"):
+    for f in ("groupnorm", "resadd", "resadd_ln", "layernorm", "geglu", "blend"):
         if f in fam:
             work = sum(d["work"] for _, d in fam[f]); ms = sum(d["ms"] for _, d in fam[f]); n = sum(d["launches"] for _, d in fam[f])
             if ms > 0:

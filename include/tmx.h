@@ -135,6 +135,21 @@ TMX_API int    tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
 TMX_API int tmx_resadd_fwd(const void* a, const void* b, void* y, size_t n, float inv_scale,
                    int dtype, void* stream);
 
+/* k6b — convolution bias folded into the ResNet tail:  y[r,c] = (a[r,c] + bias[c] + b[r,c]) * inv_scale over an
+ * NHWC [rows, C] tensor; b may be NULL (plain per-channel bias add).  Replaces the separate ATen bias-add
+ * kernel behind every [D] nn.Conv2d of ResnetBlock2D (conv2 + conv_shortcut biases travel in `bias`) and
+ * the `(input + hidden) / output_scale_factor` tail.  fp16 / bf16, C % 8 == 0; bias fp32 [C]; y may alias a or b. */
+TMX_API int tmx_bias_resadd_fwd(const void* a, const void* b, const float* bias, void* y, size_t rows, int C,
+                        float inv_scale, int dtype, void* stream);
+
+/* k6c — transformer residual add fused with the LayerNorm that consumes it ([D] BasicTransformerBlock:
+ * `hidden = attn_output + hidden; norm_hidden = self.norm2(hidden)` and the two analogous pairs):
+ *   h = round_dtype(a + b);  n = LayerNorm(h) * gamma + beta.
+ * a, b, h_out, n_out : dtype [rows, D]; h_out may alias a or b, n_out must be distinct.  D % 8 == 0, D <= 2048.
+ * Algorithmic bytes: 4 * rows * D * sizeof(dtype) (vs 5 for the two separate kernels). */
+TMX_API int tmx_resadd_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta,
+                             void* h_out, void* n_out, size_t rows, int D, float eps, int dtype, void* stream);
+
 /* k8 — LayerNorm over the last dimension ([D] BasicTransformerBlock.norm1/2/3 = F.layer_norm, fp32
  * statistics; 210 sites per U-Net forward).  x, y : dtype [rows, D] (y may alias x); gamma, beta : fp32 [D].
  * fp16 / bf16, D % 8 == 0, D <= 2048.  One pass: algorithmic bytes 2 * rows * D * sizeof(dtype). */

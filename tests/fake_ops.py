@@ -31,6 +31,27 @@ def residual_add(a, b, inv_scale=1.0, out=None):
     return y
 
 
+def bias_residual_add(a, bias, b=None, inv_scale=1.0, out=None):
+    shape = (1, -1, 1, 1) if a.dim() == 4 else (-1,)
+    y = a.float() + bias.reshape(shape)
+    if b is not None:
+        y = y + b.float()
+    y = (y * inv_scale).to(a.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def residual_add_layer_norm(a, b, gamma, beta, eps, h_out=None, n_out=None):
+    h = (a.float() + b.float()).to(a.dtype)
+    n = F.layer_norm(h.float(), (h.shape[-1],), gamma, beta, eps).to(a.dtype)
+    if h_out is not None:
+        h_out.copy_(h)
+        h = h_out
+    return h, n
+
+
 def layer_norm(x, gamma, beta, eps, out=None):
     return F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps).to(x.dtype)
 
@@ -97,5 +118,5 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
 
 def install(monkeypatch):
     from tweediemix_b200 import ops
-    for name in ("group_norm", "layer_norm", "residual_add", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish"):
+    for name in ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -231,3 +231,45 @@ def test_layernorm_errors():
         o.layer_norm(torch.zeros(2, 12, dtype=torch.bfloat16).cuda(), torch.ones(12).cuda(), torch.zeros(12).cuda(), 1e-5)
     with pytest.raises(RuntimeError, match="<= 2048"):
         o.layer_norm(torch.zeros(2, 4096, dtype=torch.bfloat16).cuda(), torch.ones(4096).cuda(), torch.zeros(4096).cuda(), 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_bias_residual_add(dtype):
+    """k6b: (a + bias[c] (+ b)) * inv_scale on channels_last tensors — fp32 sum, one rounding (bit-exact vs torch fp32)."""
+    o = ops()
+    g = torch.Generator().manual_seed(21)
+    for shape in [(4, 320, 16, 16), (2, 1280, 8, 8), (1, 8, 2, 2)]:
+        a = torch.randn(shape, generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+        b = torch.randn(shape, generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+        bias = torch.randn(shape[1], generator=g)
+        for inv in (1.0, 0.5):
+            want = ((a.float() + bias.reshape(1, -1, 1, 1) + b.float()) * inv).to(dtype)
+            got = o.bias_residual_add(a.cuda(), bias.cuda(), b.cuda(), inv).cpu()
+            assert torch.equal(got, want)
+            want1 = ((a.float() + bias.reshape(1, -1, 1, 1)) * inv).to(dtype)
+            ac = a.cuda()
+            got1 = o.bias_residual_add(ac, bias.cuda(), None, inv, out=ac).cpu()        # in place, no residual
+            assert torch.equal(got1, want1)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        o.bias_residual_add(torch.zeros(2, 6, dtype=dtype).cuda(), torch.zeros(6).cuda())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 4096, 640), (4, 1024, 1280), (3, 5, 64), (1, 1, 8), (2, 7, 2048)])
+def test_residual_add_layernorm(dtype, shape):
+    """k6c: h = round(a + b) must be bit-exact; n must equal the stand-alone LayerNorm kernel applied to h
+    bit-for-bit (same arithmetic on the same rounded row) and F.layer_norm in fp32 within one output rounding."""
+    o = ops()
+    g = torch.Generator().manual_seed(shape[-1] + 1)
+    a = (torch.randn(shape, generator=g) * 2.0).to(dtype)
+    b = (torch.randn(shape, generator=g) + 1.0).to(dtype)
+    D = shape[-1]
+    gamma, beta = 1 + 0.3 * torch.randn(D, generator=g), 0.2 * torch.randn(D, generator=g)
+    h_want = (a.float() + b.float()).to(dtype)
+    n_want = F.layer_norm(h_want.float(), (D,), gamma, beta, 1e-5)
+    ac = a.cuda()
+    h, n = o.residual_add_layer_norm(ac, b.cuda(), gamma.cuda(), beta.cuda(), 1e-5, h_out=ac)   # h aliases a
+    assert h.data_ptr() == ac.data_ptr()
+    assert torch.equal(h.cpu(), h_want)
+    torch.testing.assert_close(n.cpu().float(), n_want.to(dtype).float(), rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
+    assert torch.equal(n.cpu(), o.layer_norm(h_want.cuda(), gamma.cuda(), beta.cuda(), 1e-5).cpu())

@@ -110,6 +110,17 @@ def main():
             b_ = [torch.randn(n, device=dev, dtype=DT) for _ in range(nb)]
             us = timeit(lambda i: ops.residual_add(a[i], b_[i], out=a[i]), nb, args.reps)
             out.append(("resadd", f"n{n} x{cnt}", us, 3 * n * 2 / us / 1e3, "GB/s", hbm))
+    if want("resadd_ln"):
+        for N, D, cnt in [(4096, 640, 30), (1024, 1280, 180)]:
+            if not keep(f"N{N}_D{D}"):
+                continue
+            nb = nbuf_for(B * N * D * 8)
+            a = [torch.randn(B, N, D, device=dev, dtype=DT) for _ in range(nb)]
+            b_ = [torch.randn(B, N, D, device=dev, dtype=DT) for _ in range(nb)]
+            ns = [torch.empty(B, N, D, device=dev, dtype=DT) for _ in range(nb)]
+            g, bb = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+            us = timeit(lambda i: ops.residual_add_layer_norm(a[i], b_[i], g, bb, 1e-5, h_out=a[i], n_out=ns[i]), nb, args.reps)
+            out.append(("resadd_ln", f"N{N}_D{D} x{cnt}", us, 4 * B * N * D * 2 / us / 1e3, "GB/s", hbm))
     if want("geglu"):
         for N, D, cnt in [(4096, 640, 10), (1024, 1280, 60)]:
             nb = nbuf_for(B * N * 8 * D * 2 * 1.5)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "tmx_groupnorm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tmx_groupnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "tmx_resadd_fwd": (_i, [_vp, _vp, _vp, _sz, _f, _i, _vp]),
+    "tmx_bias_resadd_fwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),
+    "tmx_resadd_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),
     "tmx_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),
     "tmx_geglu_fwd": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
     "tmx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _f, _i, _vp]),

@@ -34,6 +34,32 @@ template <> struct Vec8<float> {
     }
 };
 
+// 4 consecutive elements: 64-bit load for 16-bit types, 128-bit for fp32.  With 4 pixels per thread every
+// load instruction of a warp covers whole 32-byte sectors (a 128-bit fp32 load per thread = 512 contiguous
+// bytes per warp), which the 8-pixel layout did not: its two half-sector fp32 loads fetched every sector
+// of x / masks twice from L2.
+template <typename T> struct Vec4 {
+    static __device__ __forceinline__ void load(const T* p, float (&f)[4]) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        float2 a = Pack2<T>::unpack(r.x), b = Pack2<T>::unpack(r.y);
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    }
+};
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+        uint4 a = ld_stream(p);
+        f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+    }
+};
+__device__ __forceinline__ void load4_f32_cached(const float* p, float (&f)[4]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+}
+__device__ __forceinline__ void store4_f32(float* p, const float (&f)[4]) {
+    st_stream(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+}
+
 __device__ __forceinline__ void load8_f32_cached(const float* p, float (&f)[8]) {
     float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -43,73 +69,91 @@ __device__ __forceinline__ void store8_f32(float* p, const float (&f)[8]) {
     st_stream(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
 }
 
-// One thread: one image, one channel, 8 consecutive pixels (a single round of independent loads:
-// at one image the kernel is pure latency, so nothing may be serialised behind a channel loop).
-template <typename T, bool REF>
+// One thread: one image, one channel, 4 consecutive pixels.  KT > 0 is the compile-time concept count
+// (all 2 + 2*K loads are issued before the first use: at one image the kernel is pure latency, at
+// thousands it must keep ~35 KB per SM in flight); KT == 0 is the generic run-time loop.
+// The Tweedie divide is a multiplication by 1/sqrt(a_t) rounded to fp32 once on the host — exactly what
+// ATen's CUDA `tensor / cpu_scalar` does (it multiplies by the reciprocal), so this is not an approximation
+// of the reference but its arithmetic.
+template <typename T, bool REF, int KT>
 __global__ void __launch_bounds__(256)
 blend_kernel(const float* __restrict__ x, const T* __restrict__ eps, const float* __restrict__ masks,
              float* __restrict__ x_out, float* __restrict__ x0_out,
              int imgs, int K, int C, int HW, const __grid_constant__ BlendCoef cf) {
-    const int groups = HW >> 3;
+    constexpr int KMAX = KT > 0 ? KT : 1;
+    const int quads = HW >> 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)imgs * C * groups) return;
-    const int p = (int)(idx % groups) << 3;
-    const int ch = (int)((idx / groups) % C);
-    const int img = (int)(idx / ((long long)groups * C));
+    if (idx >= (long long)imgs * C * quads) return;
+    const int p = (int)(idx % quads) << 2;
+    const int ch = (int)((idx / quads) % C);
+    const int img = (int)(idx / ((long long)quads * C));
+    const int Kc = KT > 0 ? KT : K;
 
     const size_t chw = (size_t)C * HW;
-    const float* xi = x + (size_t)img * chw + p;
-    const T* ei = eps + (size_t)img * (K + 1) * chw + p;
+    const size_t off = (size_t)ch * HW + p;
+    const float* xi = x + (size_t)img * chw + off;
+    const T* ei = eps + (size_t)img * (Kc + 1) * chw + off;
 
-    {
-        float xv[8], eu[8], acc[8];
-        Vec8<float>::load(xi + (size_t)ch * HW, xv);
-        Vec8<T>::load(ei + (size_t)ch * HW, eu);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float xv[4], eu[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+    Vec4<float>::load(xi, xv);
+    Vec4<T>::load(ei, eu);
 
-#pragma unroll 4
-        for (int c = 0; c < K; ++c) {
-            float ec[8], m[8];
-            Vec8<T>::load(ei + (size_t)(1 + c) * chw + (size_t)ch * HW, ec);
-            if (masks) load8_f32_cached(masks + (size_t)c * HW + p, m);
-            const float w = cf.has_w ? cf.w[c] : 1.f;
+    auto fold = [&](const float (&ec)[4], const float (&m)[4], int c) {
+        const float w = cf.has_w ? cf.w[c] : 1.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float t;
-                if (REF) {
-                    // eps dtype arithmetic exactly as torch evaluates :383 under autocast (App. B)
-                    float d = Pack2<T>::round(__fsub_rn(ec[i], eu[i]));
-                    d = Pack2<T>::round(__fmul_rn(cf.g, d));
-                    float e = Pack2<T>::round(__fadd_rn(eu[i], d));
-                    float se = Pack2<T>::round(__fmul_rn(cf.s_t, e));
-                    t = __fmul_rn(__fsub_rn(xv[i], se), cf.inv_sqrt_at);
-                    if (masks) t = __fmul_rn(m[i], t);
-                    if (cf.has_w) t = __fmul_rn(w, t);
-                    acc[i] = __fadd_rn(acc[i], t);
-                } else {
-                    float e = fmaf(cf.g, ec[i] - eu[i], eu[i]);
-                    t = (xv[i] - cf.s_t * e) / cf.sqrt_at;
-                    float mw = masks ? m[i] * w : w;
-                    acc[i] = fmaf(mw, t, acc[i]);
-                }
-            }
-        }
-        if (x0_out) store8_f32(x0_out + (size_t)img * chw + (size_t)ch * HW + p, acc);
-        float out[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (cf.is_last) {
-                out[i] = acc[i];
-            } else if (REF) {
-                float nz = Pack2<T>::round(__fmul_rn(cf.s_n, eu[i]));
-                out[i] = __fadd_rn(__fmul_rn(cf.sqrt_an, acc[i]), nz);
+        for (int i = 0; i < 4; ++i) {
+            float t;
+            if (REF) {
+                // eps dtype arithmetic exactly as torch evaluates :383 under autocast (App. B)
+                float d = Pack2<T>::round(__fsub_rn(ec[i], eu[i]));
+                d = Pack2<T>::round(__fmul_rn(cf.g, d));
+                float e = Pack2<T>::round(__fadd_rn(eu[i], d));
+                float se = Pack2<T>::round(__fmul_rn(cf.s_t, e));
+                t = __fmul_rn(__fsub_rn(xv[i], se), cf.inv_sqrt_at);
+                if (masks) t = __fmul_rn(m[i], t);
+                if (cf.has_w) t = __fmul_rn(w, t);
+                acc[i] = __fadd_rn(acc[i], t);
             } else {
-                out[i] = fmaf(cf.sqrt_an, acc[i], cf.s_n * eu[i]);
+                const float e = fmaf(cf.g, ec[i] - eu[i], eu[i]);
+                t = fmaf(-cf.s_t, e, xv[i]) * cf.inv_sqrt_at;
+                acc[i] = fmaf(masks ? m[i] * w : w, t, acc[i]);
             }
         }
-        store8_f32(x_out + (size_t)img * chw + (size_t)ch * HW + p, out);
+    };
+
+    if constexpr (KT > 0) {
+        float ec[KMAX][4], m[KMAX][4];
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+            Vec4<T>::load(ei + (size_t)(1 + c) * chw, ec[c]);
+            if (masks) load4_f32_cached(masks + (size_t)c * HW + p, m[c]);
+            else { m[c][0] = m[c][1] = m[c][2] = m[c][3] = 1.f; }
+        }
+#pragma unroll
+        for (int c = 0; c < KT; ++c) fold(ec[c], m[c], c);
+    } else {
+#pragma unroll 2
+        for (int c = 0; c < K; ++c) {
+            float ec[4], m[4] = {1.f, 1.f, 1.f, 1.f};
+            Vec4<T>::load(ei + (size_t)(1 + c) * chw, ec);
+            if (masks) load4_f32_cached(masks + (size_t)c * HW + p, m);
+            fold(ec, m, c);
+        }
     }
+    if (x0_out) store4_f32(x0_out + (size_t)img * chw + off, acc);
+    float out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (cf.is_last) {
+            out[i] = acc[i];
+        } else if (REF) {
+            float nz = Pack2<T>::round(__fmul_rn(cf.s_n, eu[i]));
+            out[i] = __fadd_rn(__fmul_rn(cf.sqrt_an, acc[i]), nz);
+        } else {
+            out[i] = fmaf(cf.sqrt_an, acc[i], cf.s_n * eu[i]);
+        }
+    }
+    store4_f32(x_out + (size_t)img * chw + off, out);
 }
 
 struct PartialRows {
@@ -191,7 +235,7 @@ blend_finish_kernel(const float* __restrict__ x, const float* __restrict__ acc, 
         Vec8<float>::load(acc + (size_t)img * 2 * chw + chw + (size_t)ch * HW + p, u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            x0[i] = (M[i] * xv[i] - k_u * M[i] * u[i] - k_a * a[i]) / cf.sqrt_at;
+            x0[i] = (M[i] * xv[i] - k_u * M[i] * u[i] - k_a * a[i]) * cf.inv_sqrt_at;
             out[i] = cf.is_last ? x0[i] : fmaf(cf.sqrt_an, x0[i], cf.s_n * u[i]);
         }
         if (x0_out) store8_f32(x0_out + (size_t)img * chw + (size_t)ch * HW + p, x0);
@@ -213,16 +257,29 @@ static BlendCoef make_coef(float a_t, float a_next, float g, int is_last, const 
     return cf;
 }
 
+template <typename T, bool REF>
+static void launch_blend_k(const float* x, const T* eps, const float* masks, float* x_out, float* x0_out,
+                           int imgs, int K, int C, int HW, const BlendCoef& cf, unsigned blocks, cudaStream_t st) {
+    switch (K) {
+        case 1: blend_kernel<T, REF, 1><<<blocks, 256, 0, st>>>(x, eps, masks, x_out, x0_out, imgs, K, C, HW, cf); break;
+        case 2: blend_kernel<T, REF, 2><<<blocks, 256, 0, st>>>(x, eps, masks, x_out, x0_out, imgs, K, C, HW, cf); break;
+        case 3: blend_kernel<T, REF, 3><<<blocks, 256, 0, st>>>(x, eps, masks, x_out, x0_out, imgs, K, C, HW, cf); break;
+        case 4: blend_kernel<T, REF, 4><<<blocks, 256, 0, st>>>(x, eps, masks, x_out, x0_out, imgs, K, C, HW, cf); break;
+        default: blend_kernel<T, REF, 0><<<blocks, 256, 0, st>>>(x, eps, masks, x_out, x0_out, imgs, K, C, HW, cf); break;
+    }
+}
+
 template <typename T>
 static int launch_blend(const float* x, const void* eps, const float* masks, float* x_out, float* x0_out,
                         int imgs, int K, int C, int HW, const BlendCoef& cf, int round_mode, cudaStream_t st) {
-    const long long total = (long long)imgs * C * (HW >> 3);
-    const int threads = 256;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    const long long total = (long long)imgs * C * (HW >> 2);
+    const long long nblk = (total + 255) / 256;
+    if (nblk > 0x7fffffffLL) { set_error("tweedie_blend: problem too large for one launch"); return TMX_ESHAPE; }
+    const unsigned blocks = (unsigned)nblk;
     if (round_mode == TMX_ROUND_REF)
-        blend_kernel<T, true><<<blocks, threads, 0, st>>>(x, (const T*)eps, masks, x_out, x0_out, imgs, K, C, HW, cf);
+        launch_blend_k<T, true>(x, (const T*)eps, masks, x_out, x0_out, imgs, K, C, HW, cf, blocks, st);
     else
-        blend_kernel<T, false><<<blocks, threads, 0, st>>>(x, (const T*)eps, masks, x_out, x0_out, imgs, K, C, HW, cf);
+        launch_blend_k<T, false>(x, (const T*)eps, masks, x_out, x0_out, imgs, K, C, HW, cf, blocks, st);
     return check_cuda(cudaGetLastError(), "blend_kernel launch");
 }
 

@@ -239,6 +239,46 @@ def residual_add(a, b, inv_scale: float = 1.0, out=None):
     return out
 
 
+def bias_residual_add(a, bias, b=None, inv_scale: float = 1.0, out=None):
+    """(a + bias[c] (+ b)) * inv_scale on channels_last 4-D (or [..., C] dense) 16-bit tensors; bias fp32 [C]."""
+    _dev(a, b, bias, out)
+    if a.dim() == 4:
+        if not a.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError("tmx.bias_residual_add: 4-D input must be channels_last")
+        Cc = a.shape[1]
+    else:
+        assert a.is_contiguous()
+        Cc = a.shape[-1]
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == Cc
+    if b is not None:
+        assert b.dtype == a.dtype and b.shape == a.shape and b.stride() == a.stride()
+    if out is None:
+        out = torch.empty_like(a)
+    assert out.stride() == a.stride()
+    rows = a.numel() // Cc
+    with _Launch("resadd", 1, "bias", (3.0 if b is not None else 2.0) * a.numel() * a.element_size()):
+        rc = _lib.load().tmx_bias_resadd_fwd(_p(a), _p(b), _p(bias), _p(out), rows, Cc, float(inv_scale), _dt(a), _stream())
+    _lib.check(rc, "tmx_bias_resadd_fwd")
+    return out
+
+
+def residual_add_layer_norm(a, b, gamma, beta, eps: float, h_out=None, n_out=None):
+    """h = a + b (stored, may alias a or b); n = LayerNorm(h) over the last dim.  Returns (h, n)."""
+    _dev(a, b, gamma, beta, h_out, n_out)
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape and a.dtype == b.dtype
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    D = a.shape[-1]
+    rows = a.numel() // D
+    if h_out is None:
+        h_out = torch.empty_like(a)
+    if n_out is None:
+        n_out = torch.empty_like(a)
+    with _Launch("resadd_ln", 1, f"D{D}", 4.0 * a.numel() * a.element_size()):
+        rc = _lib.load().tmx_resadd_layernorm_fwd(_p(a), _p(b), _p(gamma), _p(beta), _p(h_out), _p(n_out), rows, D, float(eps), _dt(a), _stream())
+    _lib.check(rc, "tmx_resadd_layernorm_fwd")
+    return h_out, n_out
+
+
 def layer_norm(x, gamma, beta, eps: float, out=None):
     """LayerNorm over the last dim of a contiguous fp16 / bf16 tensor; gamma / beta fp32 [D]."""
     _dev(x, gamma, beta, out)

@@ -275,20 +275,36 @@ class BasicTransformerBlock(nn.Module):
         return ops.layer_norm(h, p32[0], p32[1], norm.eps)
 
     @staticmethod
-    def _call_attn(attn: TmxAttention, x, ehs, residual):
+    def _p32(norm: nn.LayerNorm):
+        p32 = norm.__dict__.get("_p32")
+        if p32 is None or p32[0].device != norm.weight.device:
+            p32 = norm.__dict__["_p32"] = (norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
+        return p32
+
+    @staticmethod
+    def _call_attn(attn: TmxAttention, x, ehs):
         # A hooked module carries an instance-level ``forward`` with the reference's 3-argument
-        # signature (utils_custom.py:53); the residual is then added here instead of inside.
+        # signature (utils_custom.py:53); un-hooked modules go through nn.Module.__call__.
         hooked = attn.__dict__.get("forward")
         if hooked is None:
-            return attn(x, encoder_hidden_states=ehs, attention_mask=None, residual=residual)
-        o = hooked(x, encoder_hidden_states=ehs, attention_mask=None)
-        return ops.residual_add(o, residual, out=o)
+            return attn(x, encoder_hidden_states=ehs, attention_mask=None)
+        return hooked(x, encoder_hidden_states=ehs, attention_mask=None)
 
-    def forward(self, h, encoder_hidden_states):
-        h = self._call_attn(self.attn1, self._ln(self.norm1, h), None, h)
-        h = self._call_attn(self.attn2, self._ln(self.norm2, h), encoder_hidden_states, h)
-        f = self.ff(self._ln(self.norm3, h))
-        return ops.residual_add(f, h, out=f)
+    def _add_norm(self, o, h, norm: Optional[nn.LayerNorm]):
+        """h' = o + h (in o's storage) and, when a LayerNorm follows, n = norm(h') from the same kernel (k6c)."""
+        if norm is None:
+            return ops.residual_add(o, h, out=o), None
+        g, b = self._p32(norm)
+        return ops.residual_add_layer_norm(o, h, g, b, norm.eps, h_out=o)
+
+    def forward(self, h, encoder_hidden_states, n=None, next_norm: Optional[nn.LayerNorm] = None):
+        """``n`` = norm1(h) if the caller already has it (fused into the previous block's last add);
+        returns (h_out, next_norm(h_out) or None)."""
+        if n is None:
+            n = self._ln(self.norm1, h)
+        h, n = self._add_norm(self._call_attn(self.attn1, n, None), h, self.norm2)
+        h, n = self._add_norm(self._call_attn(self.attn2, n, encoder_hidden_states), h, self.norm3)
+        return self._add_norm(self.ff(n), h, next_norm)
 
 
 class Transformer2DModel(nn.Module):
@@ -305,8 +321,10 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, encoder_hidden_states):
         _, _, hh, ww = x.shape
         h = self.proj_in(_tokens(self.norm(x, silu=False)))
-        for blk in self.transformer_blocks:
-            h = blk(h, encoder_hidden_states)
+        n = None
+        blocks = self.transformer_blocks
+        for i, blk in enumerate(blocks):
+            h, n = blk(h, encoder_hidden_states, n, blocks[i + 1].norm1 if i + 1 < len(blocks) else None)
         h = _image(self.proj_out(h), hh, ww)
         return ops.residual_add(h, x, out=h)
 
@@ -329,12 +347,39 @@ class ResnetBlock2D(nn.Module):
         self.output_scale_factor = 1.0
         self.temb_slice_index = 0                           # set by the U-Net: which split of the packed temb GEMM
 
+    def tail_bias(self) -> torch.Tensor:
+        """fp32 conv2.bias (+ conv_shortcut.bias): added by the fused tail kernel (k6b), not by cuDNN/ATen."""
+        b = self.__dict__.get("_tail_bias")
+        if b is None or b.device != self.conv2.weight.device:
+            b = self.conv2.bias.detach().float()
+            if self.conv_shortcut is not None:
+                b = b + self.conv_shortcut.bias.detach().float()
+            b = self.__dict__["_tail_bias"] = b.contiguous()
+        return b
+
     def forward(self, x, temb_all):
-        h = self.conv1(self.norm1(x, silu=True))
-        h = self.conv2(self.norm2(h, silu=True, add=temb_all[self.temb_slice_index]))
+        # conv1.bias rides in temb_all (packed with time_emb_proj.bias), conv2/shortcut biases in the tail add
+        h = _conv_nobias(self.conv1, self.norm1(x, silu=True))
+        h = _conv_nobias(self.conv2, self.norm2(h, silu=True, add=temb_all[self.temb_slice_index]))
         if self.conv_shortcut is not None:
-            x = self.conv_shortcut(x)
-        return ops.residual_add(h, x, 1.0 / self.output_scale_factor, out=h)
+            x = _conv_nobias(self.conv_shortcut, x)
+        return ops.bias_residual_add(h, self.tail_bias(), x, 1.0 / self.output_scale_factor, out=h)
+
+
+def _conv_nobias(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """cuDNN convolution without the bias (ATen would add it in a separate elementwise launch)."""
+    return F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
+
+
+def _conv_bias(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """Convolution + per-channel bias through the vectorised tmx bias kernel (k6b with b = NULL)."""
+    b32 = conv.__dict__.get("_b32")
+    if b32 is None or b32.device != conv.weight.device:
+        b32 = conv.__dict__["_b32"] = conv.bias.detach().float().contiguous()
+    y = _conv_nobias(conv, x)
+    if y.shape[1] % 8 != 0:                       # conv_out (4 channels): not worth a kernel
+        return y + conv.bias.reshape(1, -1, 1, 1).to(y.dtype)
+    return ops.bias_residual_add(y, b32, None, 1.0, out=y)
 
 
 class Downsample2D(nn.Module):
@@ -343,7 +388,7 @@ class Downsample2D(nn.Module):
         self.conv = nn.Conv2d(c, c, 3, stride=2, padding=1)
 
     def forward(self, x):
-        return self.conv(x)
+        return _conv_bias(self.conv, x)
 
 
 class Upsample2D(nn.Module):
@@ -352,7 +397,7 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
     def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        return _conv_bias(self.conv, F.interpolate(x, scale_factor=2.0, mode="nearest"))
 
 
 class DownBlock(nn.Module):
@@ -478,12 +523,15 @@ class TmxUNet2DConditionModel(nn.Module):
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+                m.__dict__.pop("_b32", None)
             elif isinstance(m, TmxAttention):
                 m.drop_packed()
             elif isinstance(m, TmxGroupNorm):
                 m._w32 = m._b32 = None
             elif isinstance(m, nn.LayerNorm):
                 m.__dict__.pop("_p32", None)
+            elif isinstance(m, ResnetBlock2D):
+                m.__dict__.pop("_tail_bias", None)
         self._temb_w = self._temb_b = None
         return self
 
@@ -500,7 +548,8 @@ class TmxUNet2DConditionModel(nn.Module):
     def _packed_temb(self):
         if self._temb_w is None or self._temb_w.device != self.device or self._temb_w.dtype != self.dtype:
             self._temb_w = torch.cat([r.time_emb_proj.weight for r in self._resnets]).detach().contiguous()
-            self._temb_b = torch.cat([r.time_emb_proj.bias for r in self._resnets]).detach().contiguous()
+            # conv1.bias is a per-channel constant added right before norm2, exactly where temb goes: fold it in
+            self._temb_b = torch.cat([r.time_emb_proj.bias + r.conv1.bias for r in self._resnets]).detach().contiguous()
         return self._temb_w, self._temb_b
 
     def embed(self, batch: int, timestep, added_cond_kwargs) -> torch.Tensor:
@@ -521,7 +570,7 @@ class TmxUNet2DConditionModel(nn.Module):
         # one GEMM for all 17 time_emb_proj; fp32 per-(n,c) biases consumed by the GN kernel's `add`
         temb_all = [t.contiguous() for t in F.linear(F.silu(temb), w, bias).float().split(self._temb_splits, dim=1)]
         ehs = encoder_hidden_states if encoder_hidden_states.dtype == dt else encoder_hidden_states.to(dt)
-        h = self.conv_in(sample.to(dt).contiguous(memory_format=torch.channels_last))
+        h = _conv_bias(self.conv_in, sample.to(dt).contiguous(memory_format=torch.channels_last))
         skips = [h]
         for blk in self.down_blocks:
             h = blk(h, temb_all, ehs, skips)
