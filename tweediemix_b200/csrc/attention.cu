@@ -1,30 +1,33 @@
 // k1 / k2 — attention forward for head_dim 64 on sm_100a:  O = softmax(scale * Q K^T) V.
 //
 // Blackwell-native structure (no mma.sync / wgmma):
+//   * PERSISTENT: one 384-thread CTA per SM walks a contiguous, balanced range of 128-row query
+//     tiles (linear index over (b, h, q-tile)); two query tiles of the same (b, h) are processed
+//     together ("slots" 0 and 1) and share every K/V tile, a lone tile at a range or head boundary
+//     runs in slot 0 alone.  The next step's Q (double-buffered) and K/V tiles are prefetched while
+//     the current step computes, so there is no per-tile prologue bubble and the tail of the launch
+//     is at most one lone query tile per SM;
 //   * Q, K, V tiles are staged global -> shared by TMA (cp.async.bulk.tensor.4d, SWIZZLE_128B)
 //     straight from the [B, N, H, 64] tensors diffusers hands the hook, no permute;
-//   * S = Q K^T and O += P V are tcgen05.mma (kind::f16, M=128) issued by ONE elected thread,
-//     accumulators live in TMEM; P is written back to TMEM as packed 16-bit and consumed as the
-//     A operand of the second MMA (TS form), so P never touches shared memory;
-//   * warp-specialised: warp 0 = TMA producer (+ TMEM alloc), one MMA-issuer warp PER query tile
-//     (each blocks only on its own tile's barriers, so a tile that is ahead is never queued behind
-//     the other one), then one 128-thread softmax group per 128-row query tile (thread == row ==
-//     TMEM lane), all linked by mbarriers; tcgen05.commit signals MMA completion;
+//   * S = Q K^T and O += P V are tcgen05.mma (kind::f16, M=128) issued by ONE elected thread per
+//     slot, accumulators live in TMEM (512 columns: per slot S[0,128) O[128,192) P[192,256)); P is
+//     written back to TMEM as packed 16-bit and consumed as the A operand of the second MMA (TS
+//     form), so P never touches shared memory;
+//   * warp-specialised: warp 0 = TMA producer (+ TMEM alloc), warps 1-2 = MMA issuers (one per
+//     slot), warps 4-11 = two 128-thread softmax groups (thread == row == TMEM lane), linked by
+//     mbarriers; tcgen05.commit signals MMA completion.  setmaxnreg moves registers from the
+//     utility warps (56) to the softmax warps (224) so a full 128-column S row stays in registers;
 //   * online softmax in the exp2 domain with lazy rescaling of O (only when the running max
-//     moves by more than 2^8), exact because the row sum is accumulated against the same
-//     reference;
-//   * the S buffer of a query tile is released (s_free) as soon as its 128 columns sit in
-//     registers, so the tensor pipe computes S(j+1) = Q K(j+1)^T WHILE the softmax of tile j runs;
-//     P has its own TMEM columns and is guarded by pv_done (tcgen05.commit after P V);
+//     moves by more than 2^8), exact because the row sum is accumulated against the same reference;
+//   * the S buffer of a slot is released (s_free) as soon as its 128 columns sit in registers, so
+//     the tensor pipe computes S(j+1) WHILE the softmax of tile j runs (also across steps);
 //   * head dim 64 makes the kernel exp-bound, not MMA-bound: 16 MUFU.EX2 / clk / SM against 8192
-//     tensor FLOP / clk / SM is 1024 vs 512 clk per 128x128 tile (ex2.approx.f16x2 is no way out: it
-//     lowers to two MUFU.EX2.F16, checked in SASS).  kPolyEvery > 0 moves one exponential in every
-//     kPolyEvery pairs to the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error
-//     7.5e-5 << the 2^-9 rounding of P); measured neutral on B200 because the softmax warps are then
-//     issue-bound, so the default is all-MUFU.
-// NQ = query tiles per CTA.  NQ=1: 192 threads, 256 TMEM columns, two CTAs per SM overlap each
-// other's softmax and MMA phases.  NQ=2: 384 threads, 512 TMEM columns, the two tiles ping-pong on
-// the tensor pipe and share every K/V tile (half the L2->SMEM traffic).
+//     tensor FLOP / clk / SM is 1024 vs 512 clk per 128x128 tile.  The scale/subtract and the row
+//     sum use packed FFMA2 / FADD2 (two fp32 lanes per issue slot) and one pair of exponentials in
+//     every kPolyEvery pairs is evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax
+//     polynomial) to take load off the MUFU;
+//   * a partial last K/V tile (cross-attention: Nk = 77) only pays for ceil(valid/32) softmax
+//     chunks and ceil(valid/16) P V k-steps.
 //
 // Replaces the einsum -> softmax -> einsum of fusion_generation/utils_custom.py:91-105 and
 // utils_lora.py:99-113 (which materialise the [B*h, N, N] score tensor).
@@ -39,9 +42,9 @@ constexpr int kBN = 128;             // kv rows per tile     (UMMA N of QK^T, K 
 constexpr int kTileBytes = kBM * kD * 2;         // 16 KiB, one 128x64 16-bit tile
 constexpr float kRescaleThreshold = 8.0f;        // log2 domain
 #ifndef TMX_ATTN_POLY_EVERY
-#define TMX_ATTN_POLY_EVERY 0
+#define TMX_ATTN_POLY_EVERY 4
 #endif
-constexpr int kPolyEvery = TMX_ATTN_POLY_EVERY;  // of every kPolyEvery PAIRS of exponentials one goes to the FMA pipe (0 = all MUFU): 2 -> 25 %
+constexpr int kPolyEvery = TMX_ATTN_POLY_EVERY;  // one PAIR of exponentials in every kPolyEvery pairs goes to the FMA pipe (0 = all MUFU)
 
 __device__ unsigned int g_attn_timeout_flag = 0;
 
@@ -66,14 +69,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must end in a trap (CUDA error), never in a hung GPU.
+// Bounded wait: a protocol bug must end in a trap (CUDA error), never in a hung GPU.  try_wait suspends
+// the warp in hardware for a while, so the loop body is rarely executed; the clock is only read
+// every 256 failed polls to keep the spinning warps off the issue ports of the softmax warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
+    long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {            // ~2 s
-            atomicExch(&g_attn_timeout_flag, 1u);
-            __trap();
+        if ((++polls & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) {          // ~2 s
+                atomicExch(&g_attn_timeout_flag, 1u);
+                __trap();
+            }
         }
     }
 }
@@ -149,17 +159,46 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-// 2^x on the FMA/ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
-// 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5), 2^n by adding n to the exponent field.
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.f);
-    const float magic = 12582912.f;                      // 1.5 * 2^23: low mantissa bits of (x + magic) hold round(x)
-    const float xr = x + magic;
-    const float f = x - (xr - magic);
-    float p = fmaf(f, 0.05517132208f, 0.24261054397f);   // minimax of 2^f on [-0.5, 0.5], max rel. error 7.5e-5
-    p = fmaf(p, f, 0.69326096773f);
-    p = fmaf(p, f, 0.99992811680f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 process two fp32 lanes per issue slot) ----
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// 2^x for a PAIR on the FMA/ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max rel. error 7.5e-5 << the 2^-9 / 2^-12 rounding of P),
+// 2^n by adding n to the exponent field.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& e0, float& e1) {
+    float x0, x1;
+    upk2(x2, x0, x1);
+    x0 = fmaxf(x0, -126.f);
+    x1 = fmaxf(x1, -126.f);
+    x2 = pk2(x0, x1);
+    const uint64_t xr = fadd2(x2, pk2(12582912.f, 12582912.f));          // 1.5 * 2^23: low mantissa bits hold round(x)
+    const uint64_t t = fadd2(xr, pk2(-12582912.f, -12582912.f));         // round(x) as a float
+    const uint64_t f = ffma2(t, pk2(-1.f, -1.f), x2);                    // x - round(x)
+    uint64_t p = ffma2(f, pk2(0.05517132208f, 0.05517132208f), pk2(0.24261054397f, 0.24261054397f));
+    p = ffma2(p, f, pk2(0.69326096773f, 0.69326096773f));
+    p = ffma2(p, f, pk2(0.99992811680f, 0.99992811680f));
+    float p0, p1, r0, r1;
+    upk2(p, p0, p1);
+    upk2(xr, r0, r1);
+    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
 
 // ------------------------------------------------------------------------- UMMA descriptors
@@ -197,223 +236,325 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // ------------------------------------------------------------------------------------- kernel
-template <int NQ> struct AttnCfg {
-    static constexpr int kStages = NQ == 1 ? 2 : 3;
-    static constexpr int kFirstSoftmaxWarp = NQ == 1 ? 2 : 4;      // warps: 0 TMA, 1..NQ MMA issuers, (pad), softmax groups
-    static constexpr int kThreads = 32 * kFirstSoftmaxWarp + 128 * NQ;
-    static constexpr int kTmemCols = 256 * NQ;                     // per tile: S[0,128) O[128,192) P[192,256)
-    static constexpr int kBars = 5 * NQ + 4 * kStages;             // q_full,s_full,s_free,p_full,pv_done + k/v full/empty
-    static constexpr int kSmemBytes = 1024 /*align slack*/ + (NQ + 2 * kStages) * kTileBytes + kBars * 8 + 16;
-};
+constexpr int kSlots = 2;            // query tiles processed together by one CTA
+constexpr int kStages = 3;           // K/V ring depth
+constexpr int kQBufs = 2;            // Q double buffer (per slot)
+constexpr int kThreads = 384;        // warps: 0 TMA, 1-2 MMA issuers, 3 idle, 4-7 softmax slot 0, 8-11 softmax slot 1
+constexpr int kFirstSoftmaxWarp = 4;
+constexpr int kTmemCols = 512;
+constexpr int kRegsUtil = 56, kRegsSoftmax = 224;           // 128*56 + 256*224 = 64512 = 384*168
+constexpr int kBars = 6 * kSlots + 2 * kQBufs * kSlots + 4 * kStages;
+constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages) * kTileBytes + kBars * 8 + 16;
 
-template <int NQ, bool BF16>
-__global__ void __launch_bounds__(AttnCfg<NQ>::kThreads, NQ == 1 ? 2 : 1)
+// One scheduling step of a CTA: query tile `qt` (and qt+1 when nslots == 2) of head h, batch b.
+struct Step { int b, h, qt, nslots; };
+
+// Walk the CTA's range [it, end) of linear query-tile ids; QT = query tiles per (b, h).
+__device__ __forceinline__ bool next_step(int& it, int end, int QT, int H, int pair, Step& s) {
+    if (it >= end) return false;
+    const int bh = it / QT;
+    s.qt = it - bh * QT;
+    s.b = bh / H;
+    s.h = bh - s.b * H;
+    s.nslots = (pair && it + 1 < end && s.qt + 1 < QT) ? 2 : 1;
+    it += s.nslots;
+    return true;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, void* __restrict__ o_ptr, long long o_stride_n,
-                int Nq, int Nk, int H, float scale_log2) {
-    using Cfg = AttnCfg<NQ>;
-    constexpr int ST = Cfg::kStages;
+                int Nq, int Nk, int H, int QT, int total_tiles, int pair, float scale_log2) {
+    constexpr int ST = kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + NQ * kTileBytes;
-    uint8_t* sV = sK + ST * kTileBytes;
+    uint8_t* sQ = smem;                                   // [kQBufs][kSlots] tiles
+    uint8_t* sK = sQ + kQBufs * kSlots * kTileBytes;      // [ST]
+    uint8_t* sV = sK + ST * kTileBytes;                   // [ST]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * kTileBytes);
-    uint64_t* q_full = bars;                   // [NQ]  TMA -> MMA       : Q tile landed
-    uint64_t* s_full = q_full + NQ;            // [NQ]  MMA -> softmax   : S(j) = Q K(j)^T complete
-    uint64_t* s_free = s_full + NQ;            // [NQ]  softmax -> MMA   : S(j) copied to registers, buffer reusable
-    uint64_t* p_full = s_free + NQ;            // [NQ]  softmax -> MMA   : P(j) written to TMEM
-    uint64_t* pv_done = p_full + NQ;           // [NQ]  MMA -> softmax   : O += P(j) V(j) complete (P buffer / O readable)
-    uint64_t* k_full = pv_done + NQ;           // [ST]
+    uint64_t* q_full = bars;                              // [kQBufs*kSlots]  TMA -> MMA : Q tile landed
+    uint64_t* q_empty = q_full + kQBufs * kSlots;         // [kQBufs*kSlots]  MMA -> TMA : last S = Q K^T of the step done
+    uint64_t* s_full = q_empty + kQBufs * kSlots;         // [kSlots]  MMA -> softmax   : S(n) complete
+    uint64_t* s_free = s_full + kSlots;                   // [kSlots]  softmax -> MMA   : S(n) copied to registers
+    uint64_t* p_full = s_free + kSlots;                   // [kSlots]  softmax -> MMA   : P(n) written to TMEM
+    uint64_t* pv_done = p_full + kSlots;                  // [kSlots]  MMA -> softmax   : O += P(n) V(n) complete
+    uint64_t* k_full = pv_done + kSlots;                  // [ST]
     uint64_t* k_empty = k_full + ST;
     uint64_t* v_full = k_empty + ST;
     uint64_t* v_empty = v_full + ST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + ST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * (kBM * NQ), h = blockIdx.y, b = blockIdx.z;
-    const int T = (Nk + kBN - 1) / kBN;
+    const int T = (Nk + kBN - 1) / kBN;                   // K/V tiles per step
+    const int last_valid = Nk - (T - 1) * kBN;            // valid kv rows of the last tile (1..128)
+    const int tile_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
+    const int tile_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
-        for (int i = 0; i < ST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], NQ); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], NQ); }
+        for (int i = 0; i < kQBufs * kSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+        for (int i = 0; i < ST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], kSlots); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], kSlots); }
         fence_barrier_init();
     }
     if (warp == 0) {
         if (lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
         __syncwarp();
-        tmem_alloc(tmem_slot, Cfg::kTmemCols);
+        tmem_alloc(tmem_slot, kTmemCols);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            for (int w = 0; w < NQ; ++w) {
-                mbar_expect_tx(&q_full[w], kTileBytes);
-                tma_load_4d(sQ + w * kTileBytes, &tm_q, &q_full[w], 0, h, q0 + w * kBM, b);
-            }
-            for (int j = 0; j < T; ++j) {
-                const int st = j % ST;
-                const uint32_t ph = (uint32_t)(j / ST) & 1u;
-                mbar_wait(&k_empty[st], ph ^ 1u);
-                mbar_expect_tx(&k_full[st], kTileBytes);
-                tma_load_4d(sK + st * kTileBytes, &tm_k, &k_full[st], 0, h, j * kBN, b);
-                mbar_wait(&v_empty[st], ph ^ 1u);
-                mbar_expect_tx(&v_full[st], kTileBytes);
-                tma_load_4d(sV + st * kTileBytes, &tm_v, &v_full[st], 0, h, j * kBN, b);
-            }
-        }
-    } else if (warp <= NQ) {
-        // ================================ MMA issuer of query tile w ===================
-        if (lane == 0) {
-            const int w = warp - 1;
-            constexpr uint32_t idesc_qk = make_idesc(BF16, BF16, kBM, kBN, false);
-            constexpr uint32_t idesc_pv = make_idesc(BF16, BF16, kBM, kD, true);
-            const uint32_t t_s = tmem_base + w * 256, t_o = t_s + 128, t_p = t_s + 192;
-            const uint32_t a0 = smem_u32(sQ + w * kTileBytes);
-            auto issue_qk = [&](int st) {
-                const uint32_t b0 = smem_u32(sK + st * kTileBytes);
-#pragma unroll
-                for (int k = 0; k < kD / 16; ++k)                    // 4 x (K = 16): +32 B inside the 128 B swizzle row
-                    umma_ss(t_s, make_sw128_desc(a0 + k * 32, 16, 1024), make_sw128_desc(b0 + k * 32, 16, 1024), idesc_qk, k > 0);
-            };
-            auto issue_pv = [&](int st, bool acc) {
-                const uint32_t b0 = smem_u32(sV + st * kTileBytes);
-#pragma unroll
-                for (int k = 0; k < kBN / 16; ++k)                   // 8 x (K = 16 kv rows): +2048 B in V, +8 columns in P
-                    umma_ts(t_o, t_p + k * 8, make_sw128_desc(b0 + k * 2048, 16, 1024), idesc_pv, (acc || k > 0) ? 1u : 0u);
-            };
-            mbar_wait(&k_full[0], 0);
-            mbar_wait(&q_full[w], 0);
-            tc_fence_after();
-            issue_qk(0);
-            umma_commit(&s_full[w]);
-            umma_commit(&k_empty[0]);
-            for (int j = 0; j < T; ++j) {
-                const int st = j % ST, stn = (j + 1) % ST;
-                const uint32_t ph = (uint32_t)(j / ST) & 1u, phn = (uint32_t)((j + 1) / ST) & 1u;
-                if (j + 1 < T) {
-                    // S(j+1) as soon as the softmax group holds S(j) in registers: overlaps its exp phase
-                    mbar_wait(&k_full[stn], phn);
-                    mbar_wait(&s_free[w], (uint32_t)j & 1u);
-                    tc_fence_after();
-                    issue_qk(stn);
-                    umma_commit(&s_full[w]);
-                    umma_commit(&k_empty[stn]);
+    if (warp < kFirstSoftmaxWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegsUtil));
+        if (warp == 0) {
+            // ================================ TMA producer ================================
+            if (lane == 0) {
+                int it = tile_begin;
+                Step cur;
+                uint32_t sidx = 0, qbits = 0;                // per (buffer, slot) use parity
+                int st = 0;
+                uint32_t ph = 0;
+                while (next_step(it, tile_end, QT, H, pair, cur)) {
+                    const int buf = (int)(sidx & 1u);
+                    for (int w = 0; w < cur.nslots; ++w) {
+                        const int qi = buf * kSlots + w;
+                        mbar_wait(&q_empty[qi], ((qbits >> qi) & 1u) ^ 1u);
+                        qbits ^= 1u << qi;
+                        mbar_expect_tx(&q_full[qi], kTileBytes);
+                        tma_load_4d(sQ + qi * kTileBytes, &tm_q, &q_full[qi], 0, cur.h, (cur.qt + w) * kBM, cur.b);
+                    }
+                    for (int j = 0; j < T; ++j) {
+                        mbar_wait(&k_empty[st], ph ^ 1u);
+                        mbar_expect_tx(&k_full[st], kTileBytes);
+                        tma_load_4d(sK + st * kTileBytes, &tm_k, &k_full[st], 0, cur.h, j * kBN, cur.b);
+                        mbar_wait(&v_empty[st], ph ^ 1u);
+                        mbar_expect_tx(&v_full[st], kTileBytes);
+                        tma_load_4d(sV + st * kTileBytes, &tm_v, &v_full[st], 0, cur.h, j * kBN, cur.b);
+                        if (++st == ST) { st = 0; ph ^= 1u; }
+                    }
+                    ++sidx;
                 }
-                mbar_wait(&v_full[st], ph);
-                mbar_wait(&p_full[w], (uint32_t)j & 1u);
-                tc_fence_after();
-                issue_pv(st, j > 0);
-                umma_commit(&pv_done[w]);
-                umma_commit(&v_empty[st]);
+            }
+        } else if (warp <= kSlots) {
+            // ================================ MMA issuer of slot w ========================
+            // Walks the CTA's K/V stream tile by tile.  For every tile it first issues S = Q K^T of the
+            // NEXT tile in the stream (possibly the first tile of the next step: cross-step prefetch),
+            // then O += P V of the current one.  In a step where this slot has no query tile it only
+            // releases the K/V stages on the slot's behalf.
+            if (lane == 0) {
+                const int w = warp - 1;
+                constexpr uint32_t idesc_qk = make_idesc(BF16, BF16, kBM, kBN, false);
+                constexpr uint32_t idesc_pv = make_idesc(BF16, BF16, kBM, kD, true);
+                const uint32_t t_s = tmem_base + w * 256, t_o = t_s + 128, t_p = t_s + 192;
+                const int last_ksteps = (last_valid + 15) >> 4;
+                auto issue_qk = [&](int qi, int stage) {
+                    const uint32_t a0 = smem_u32(sQ + qi * kTileBytes);
+                    const uint32_t b0 = smem_u32(sK + stage * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kD / 16; ++k)                    // 4 x (K = 16): +32 B inside the 128 B swizzle row
+                        umma_ss(t_s, make_sw128_desc(a0 + k * 32, 16, 1024), make_sw128_desc(b0 + k * 32, 16, 1024), idesc_qk, k > 0);
+                };
+                auto issue_pv = [&](int stage, bool acc, int ksteps) {
+                    const uint32_t b0 = smem_u32(sV + stage * kTileBytes);
+                    for (int k = 0; k < ksteps; ++k)                     // (K = 16 kv rows): +2048 B in V, +8 columns in P
+                        umma_ts(t_o, t_p + k * 8, make_sw128_desc(b0 + k * 2048, 16, 1024), idesc_pv, (acc || k > 0) ? 1u : 0u);
+                };
+                int it = tile_begin;
+                Step cur, nxt;
+                bool has_cur = next_step(it, tile_end, QT, H, pair, cur);
+                uint32_t nS = 0, nPV = 0, sidx = 0, qbits = 0;   // qbits: per Q buffer use parity of this slot
+                int st = 0;                     // stage / phase of the CURRENT tile of the stream
+                uint32_t ph = 0;
+                if (has_cur) {                  // prologue: S of the very first tile
+                    mbar_wait(&k_full[0], 0);
+                    if (w < cur.nslots) {
+                        mbar_wait(&q_full[w], 0);
+                        qbits ^= 1u;
+                        tc_fence_after();
+                        issue_qk(w, 0);
+                        umma_commit(&s_full[w]);
+                        umma_commit(&k_empty[0]);
+                        ++nS;
+                        if (T == 1) umma_commit(&q_empty[w]);
+                    } else {
+                        mbar_arrive(&k_empty[0]);
+                    }
+                }
+                while (has_cur) {
+                    const bool has_nxt = next_step(it, tile_end, QT, H, pair, nxt);
+                    const bool act = w < cur.nslots;
+                    const int buf = (int)(sidx & 1u);
+                    for (int j = 0; j < T; ++j) {
+                        const bool last = (j == T - 1);
+                        if (!last || has_nxt) {
+                            int sn = st + 1;
+                            uint32_t pn = ph;
+                            if (sn == ST) { sn = 0; pn ^= 1u; }
+                            const bool nact = last ? (w < nxt.nslots) : act;
+                            mbar_wait(&k_full[sn], pn);
+                            if (nact) {
+                                const int nb = last ? (buf ^ 1) : buf;
+                                const int qi = nb * kSlots + w;
+                                if (last) { mbar_wait(&q_full[qi], (qbits >> nb) & 1u); qbits ^= 1u << nb; }
+                                if (nS > 0) mbar_wait(&s_free[w], (nS - 1u) & 1u);
+                                tc_fence_after();
+                                issue_qk(qi, sn);
+                                umma_commit(&s_full[w]);
+                                umma_commit(&k_empty[sn]);
+                                ++nS;
+                                const bool last_qk_of_step = last ? (T == 1) : (j + 1 == T - 1);
+                                if (last_qk_of_step) umma_commit(&q_empty[qi]);
+                            } else {
+                                mbar_arrive(&k_empty[sn]);
+                            }
+                        }
+                        mbar_wait(&v_full[st], ph);
+                        if (act) {
+                            mbar_wait(&p_full[w], nPV & 1u);
+                            tc_fence_after();
+                            issue_pv(st, j > 0, last ? last_ksteps : kBN / 16);
+                            umma_commit(&pv_done[w]);
+                            umma_commit(&v_empty[st]);
+                            ++nPV;
+                        } else {
+                            mbar_arrive(&v_empty[st]);
+                        }
+                        if (++st == ST) { st = 0; ph ^= 1u; }
+                    }
+                    cur = nxt;
+                    has_cur = has_nxt;
+                    ++sidx;
+                }
             }
         }
-    } else if (warp >= Cfg::kFirstSoftmaxWarp) {
+    } else {
         // ================================ softmax / correction / epilogue ==============
-        const int w = (warp - Cfg::kFirstSoftmaxWarp) >> 2;  // query tile handled by this warp group
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegsSoftmax));
+        const int w = (warp - kFirstSoftmaxWarp) >> 2;       // slot handled by this warp group
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;                 // row in the tile == TMEM lane
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + w * 256;
-        float m_ref = -INFINITY;                             // running reference max, log2 domain (scaled)
-        float l_sum = 0.f;
-
-        for (int j = 0; j < T; ++j) {
-            mbar_wait(&s_full[w], (uint32_t)j & 1u);
-            tc_fence_after();
-            uint32_t s[128];
-            tmem_ld32(t_row + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-            tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-            tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
-            tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
-            tc_wait_ld();
-            tc_fence_before();
-            mbar_arrive(&s_free[w]);                                   // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
-            const int valid = Nk - j * kBN;
-            if (valid < kBN) {
-#pragma unroll
-                for (int c = 0; c < 128; ++c) if (c >= valid) s[c] = 0xff800000u;   // -inf
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 128; c += 4) {
-                mx0 = fmaxf(mx0, __uint_as_float(s[c])); mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(s[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
-            }
-            const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-            // lazy rescale: move the reference only when the max grew by more than 2^8
-            const bool bump = m_tile > m_ref + kRescaleThreshold;
-            const float m_new = bump ? m_tile : m_ref;
-            bool pv_waited = false;
-            if (j > 0 && __any_sync(0xffffffffu, bump)) {            // warp-uniform: tcgen05.ld/st are warp-collective
-                mbar_wait(&pv_done[w], (uint32_t)(j - 1) & 1u);      // O must hold every P V issued so far
+        const uint64_t sc2 = pk2(scale_log2, scale_log2);
+        const int last_chunks = (last_valid + 31) >> 5;
+        uint32_t n = 0;                                      // tiles processed by this slot (barrier phases)
+        int it = tile_begin;
+        Step cur;
+        while (next_step(it, tile_end, QT, H, pair, cur)) {
+            if (w >= cur.nslots) continue;
+            float m_ref = -INFINITY;                         // running reference max, log2 domain (scaled)
+            float l_sum = 0.f;
+            for (int j = 0; j < T; ++j, ++n) {
+                mbar_wait(&s_full[w], n & 1u);
                 tc_fence_after();
-                pv_waited = true;
-                const float alpha = bump ? ex2(m_ref - m_new) : 1.f;
-                l_sum *= alpha;
+                uint32_t s[128];
+                tmem_ld32(t_row + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+                tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+                tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+                tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&s_free[w]);                                   // S(n) is in registers: the MMA warp may overwrite it
+                const bool last = (j == T - 1);
+                const int chunks = last ? last_chunks : 4;
+                if (last && last_valid < kBN) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t o[32];
-                    tmem_ld32(t_row + 128 + half * 32, o);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-                    tmem_st32(t_row + 128 + half * 32, o);
+                    for (int c = 0; c < 128; ++c) if (c >= last_valid) s[c] = 0xff800000u;   // -inf
                 }
-            }
-            m_ref = m_new;
-            float sum0 = 0.f, sum1 = 0.f;
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t p[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float x0 = fmaf(__uint_as_float(s[q * 32 + 2 * c]), scale_log2, -m_new);
-                    const float x1 = fmaf(__uint_as_float(s[q * 32 + 2 * c + 1]), scale_log2, -m_new);
-                    const float e0 = ex2(x0);
-                    const float e1 = (kPolyEvery > 0 && (c % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(x1) : ex2(x1);
-                    sum0 += e0; sum1 += e1;
-                    p[c] = pack2<BF16>(e0, e1);
+                for (int c = 0; c < 128; c += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[c])); mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
                 }
-                if (q == 0 && j > 0 && !pv_waited) {                   // P(j-1) must have been consumed before it is overwritten
-                    mbar_wait(&pv_done[w], (uint32_t)(j - 1) & 1u);
+                const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+                // lazy rescale: move the reference only when the max grew by more than 2^8
+                const bool bump = m_tile > m_ref + kRescaleThreshold;
+                const float m_new = bump ? m_tile : m_ref;
+                bool pv_waited = false;
+                if (j > 0 && __any_sync(0xffffffffu, bump)) {            // warp-uniform: tcgen05.ld/st are warp-collective
+                    mbar_wait(&pv_done[w], (n - 1u) & 1u);               // O must hold every P V issued so far
                     tc_fence_after();
+                    pv_waited = true;
+                    const float alpha = bump ? ex2(m_ref - m_new) : 1.f;
+                    l_sum *= alpha;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t o[32];
+                        tmem_ld32(t_row + 128 + half * 32, o);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                        tmem_st32(t_row + 128 + half * 32, o);
+                    }
                 }
-                tmem_st16(t_row + 192 + q * 16, p);
+                m_ref = m_new;
+                const uint64_t nm2 = pk2(-m_new, -m_new);
+                uint64_t sum_a = pk2(0.f, 0.f), sum_b = pk2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < chunks) {
+                        uint32_t p[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const uint64_t x2 = ffma2(pk2(__uint_as_float(s[q * 32 + 2 * c]), __uint_as_float(s[q * 32 + 2 * c + 1])), sc2, nm2);
+                            float e0, e1;
+                            if (kPolyEvery > 0 && (c % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+                                ex2_poly2(x2, e0, e1);
+                            } else {
+                                float x0, x1;
+                                upk2(x2, x0, x1);
+                                e0 = ex2(x0);
+                                e1 = ex2(x1);
+                            }
+                            if (c & 1) sum_b = fadd2(sum_b, pk2(e0, e1)); else sum_a = fadd2(sum_a, pk2(e0, e1));
+                            p[c] = pack2<BF16>(e0, e1);
+                        }
+                        if (q == 0 && j > 0 && !pv_waited) {               // P(n-1) must have been consumed before it is overwritten
+                            mbar_wait(&pv_done[w], (n - 1u) & 1u);
+                            tc_fence_after();
+                        }
+                        tmem_st16(t_row + 192 + q * 16, p);
+                    }
+                }
+                {
+                    float a0, a1, b0, b1;
+                    upk2(sum_a, a0, a1);
+                    upk2(sum_b, b0, b1);
+                    l_sum += (a0 + a1) + (b0 + b1);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&p_full[w]);
             }
-            l_sum += sum0 + sum1;
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(&p_full[w]);
-        }
 
-        // epilogue: O / l -> global (row-contiguous 128 B per thread)
-        mbar_wait(&pv_done[w], (uint32_t)(T - 1) & 1u);
-        tc_fence_after();
-        const float inv_l = 1.f / l_sum;
-        const int q_row = q0 + w * kBM + row;
-        uint8_t* dst = reinterpret_cast<uint8_t*>(o_ptr) +
-                       (((size_t)b * Nq + (size_t)q_row) * (size_t)o_stride_n + (size_t)h * kD) * 2;
+            // epilogue: O / l -> global (row-contiguous 128 B per thread)
+            mbar_wait(&pv_done[w], (n - 1u) & 1u);
+            tc_fence_after();
+            const float inv_l = 1.f / l_sum;
+            const int q_row = (cur.qt + w) * kBM + row;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(o_ptr) +
+                           (((size_t)cur.b * Nq + (size_t)q_row) * (size_t)o_stride_n + (size_t)cur.h * kD) * 2;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t o[32];
-            tmem_ld32(t_row + 128 + half * 32, o);
-            tc_wait_ld();
-            if (q_row < Nq) {
+            for (int half = 0; half < 2; ++half) {
+                uint32_t o[32];
+                tmem_ld32(t_row + 128 + half * 32, o);
+                tc_wait_ld();
+                if (q_row < Nq) {
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    uint4 v;
-                    v.x = pack2<BF16>(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-                    v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-                    v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-                    v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(dst + (half * 32 + c) * 2) = v;
+                    for (int c = 0; c < 32; c += 8) {
+                        uint4 v;
+                        v.x = pack2<BF16>(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+                        v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+                        v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+                        v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(dst + (half * 32 + c) * 2) = v;
+                    }
                 }
             }
+            tc_fence_before();           // order the O reads before the next step's P(0) hand-off (p_full arrive)
         }
     }
 
@@ -421,7 +562,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -439,10 +580,8 @@ int attn_init() {
         TMX_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, TMX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
         g_encode = (EncodeTiledFn)fn;
     }
-    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1>::kSmemBytes));
-    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1>::kSmemBytes));
-    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<2>::kSmemBytes));
-    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<2>::kSmemBytes));
+    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     return TMX_OK;
 }
 
@@ -459,7 +598,7 @@ static int make_map(CUtensorMap* m, const void* base, int B, int N, int H, int64
     return TMX_OK;
 }
 
-static int g_force_nq = 0;   // test hook: 0 = heuristic
+static int g_variant = 0;   // test hook: 0 / 2 = pair query tiles (default), 1 = one query tile per step
 
 }  // namespace tmx
 
@@ -467,7 +606,7 @@ using namespace tmx;
 
 extern "C" int tmx_attn_set_variant(int nq) {
     TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1 or 2");
-    g_force_nq = nq;
+    g_variant = nq;
     return TMX_OK;
 }
 
@@ -479,13 +618,16 @@ extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o
     TMX_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, TMX_EINVAL, "attn: non-positive size");
     TMX_REQUIRE(D == kD, TMX_ESHAPE, "attn: head dim %d unsupported (only 64)", D);
     TMX_REQUIRE(dtype == TMX_F16 || dtype == TMX_BF16, TMX_EDTYPE, "attn: dtype %d unsupported (fp16/bf16 only)", dtype);
-    TMX_REQUIRE(B <= 65535 && H <= 65535, TMX_ESHAPE, "attn: B or H too large for the grid");
+    TMX_REQUIRE(scale > 0.f, TMX_EINVAL, "attn: scale must be positive");
     const int64_t hd = (int64_t)H * kD;
     TMX_REQUIRE(q_stride_n >= hd && k_stride_n >= hd && v_stride_n >= hd && o_stride_n >= hd, TMX_ESHAPE,
                 "attn: token stride smaller than H*64");
     TMX_REQUIRE(q_stride_n % 8 == 0 && k_stride_n % 8 == 0 && v_stride_n % 8 == 0 && o_stride_n % 8 == 0, TMX_EALIGN,
                 "attn: token strides must be multiples of 8 elements");
     TMX_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), TMX_EALIGN, "attn: 16-byte alignment");
+    const int QT = (Nq + kBM - 1) / kBM;
+    const long long total = (long long)B * H * QT;
+    TMX_REQUIRE(total < (1ll << 30), TMX_ESHAPE, "attn: too many query tiles");
     if (int rc = require_init()) return rc;
 
     const bool bf16 = dtype == TMX_BF16;
@@ -495,16 +637,11 @@ extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (int rc = make_map(&mv, v, B, Nk, H, v_stride_n, bf16)) return rc;
     const float scale_log2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
-    // two query tiles per CTA when there is enough work to fill the machine with them
-    int nq = g_force_nq ? g_force_nq : ((Nq > kBM && (long long)B * H * ((Nq + 255) / 256) >= sm_count()) ? 2 : 1);
-    if (nq == 2) {
-        dim3 grid((Nq + 2 * kBM - 1) / (2 * kBM), H, B);
-        if (bf16) attn_fwd_kernel<2, true><<<grid, AttnCfg<2>::kThreads, AttnCfg<2>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
-        else      attn_fwd_kernel<2, false><<<grid, AttnCfg<2>::kThreads, AttnCfg<2>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
-    } else {
-        dim3 grid((Nq + kBM - 1) / kBM, H, B);
-        if (bf16) attn_fwd_kernel<1, true><<<grid, AttnCfg<1>::kThreads, AttnCfg<1>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
-        else      attn_fwd_kernel<1, false><<<grid, AttnCfg<1>::kThreads, AttnCfg<1>::kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, scale_log2);
-    }
+    const int pair = g_variant == 1 ? 0 : 1;
+    // persistent grid: one CTA per SM, never more CTAs than (pairs of) query tiles
+    const long long units = pair ? (total + 1) / 2 : total;
+    const int grid = (int)(units < sm_count() ? units : sm_count());
+    if (bf16) attn_fwd_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, QT, (int)total, pair, scale_log2);
+    else      attn_fwd_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, QT, (int)total, pair, scale_log2);
     return check_cuda(cudaGetLastError(), "attn_fwd_kernel launch");
 }
