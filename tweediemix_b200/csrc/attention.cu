@@ -48,31 +48,45 @@ constexpr int kPolyEvery = TMX_ATTN_POLY_EVERY;  // one PAIR of exponentials in 
 
 __device__ unsigned int g_attn_timeout_flag = 0;
 
+// Optional event trace of CTA 0 (debug builds only: -DTMX_ATTN_TRACE): role r in {0 TMA, 1 MMA slot 0, 2 softmax
+// slot 0 / half 0 / quarter 0} appends (tag, clock64) pairs; read back with tmx_attn_debug_trace().
+#ifdef TMX_ATTN_TRACE
+constexpr int kTraceLen = 4096;
+__device__ long long g_attn_trace[4][kTraceLen];
+#define TMX_TRACE_DECL(role, cond) const bool trace_on_ = (cond) && blockIdx.x == 0; int trace_n_ = 0; constexpr int trace_role_ = (role);
+#define TMX_TRACE(tag) do { if (trace_on_ && trace_n_ + 2 <= kTraceLen) { g_attn_trace[trace_role_][trace_n_++] = (tag); g_attn_trace[trace_role_][trace_n_++] = clock64(); } } while (0)
+#else
+#define TMX_TRACE_DECL(role, cond)
+#define TMX_TRACE(tag) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+// All mbarrier helpers take the 32-bit shared-window address (computed ONCE per kernel from the generic
+// pointer): a generic->shared conversion per call costs an S2UR + ULEA chain in every hot loop.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must end in a trap (CUDA error), never in a hung GPU.  try_wait suspends
 // the warp in hardware for a while, so the loop body is rarely executed; the clock is only read
 // every 256 failed polls to keep the spinning warps off the issue ports of the softmax warps.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t polls = 0;
     long long t0 = 0;
@@ -87,6 +101,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// One lane of a CONVERGED warp (cute::elect_one_sync): keeps the operands of the guarded tcgen05 / TMA
+// instructions warp-uniform for the compiler, so they live in uniform registers instead of being
+// funnelled through a per-instruction R2UR "uniformisation" loop (measured: ~170 clk per tcgen05.mma).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -96,23 +122,23 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar,
                                             int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
+        :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar),
            "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(ncols) : "memory");
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -127,6 +153,31 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Same, with descriptors given as their LOW words (start address + LBO); the high word (SBO = 1024 B,
+// version 1, SWIZZLE_128B) is the same for every operand tile of this kernel.  Keeping the per-MMA
+// arithmetic to one add on a precomputed low word matters: the issuing thread works in the slow uniform
+// datapath, and a shift/mask/or chain per descriptor cost ~70 clk per tcgen05.mma.
+constexpr uint32_t kDescHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | ((16u >> 4) << 16); }
+template <bool ACC>
+__device__ __forceinline__ void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_addr) : "memory");
 }
 
 #define TMX_R8(r, o)  "=r"(r[o+0]), "=r"(r[o+1]), "=r"(r[o+2]), "=r"(r[o+3]), "=r"(r[o+4]), "=r"(r[o+5]), "=r"(r[o+6]), "=r"(r[o+7])
@@ -239,12 +290,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 constexpr int kSlots = 2;            // query tiles processed together by one CTA
 constexpr int kStages = 3;           // K/V ring depth
 constexpr int kQBufs = 2;            // Q double buffer (per slot)
-constexpr int kThreads = 384;        // warps: 0 TMA, 1-2 MMA issuers, 3 idle, 4-7 softmax slot 0, 8-11 softmax slot 1
-constexpr int kFirstSoftmaxWarp = 4;
+constexpr int kThreads = 640;        // warps 0-15 softmax: (0-3, 8-11) slot 0, (4-7, 12-15) slot 1; 16 TMA, 17 QK issuer, 18-19 PV issuers
+constexpr int kUtilWarp = 16;        // utility warps sit at the HIGHEST warp ids: the SMSP arbiter favours them, so a ready MMA issue / TMA
+                                     // instruction is never queued behind the 4 busy softmax warps of its SMSP
 constexpr int kTmemCols = 512;
-constexpr int kRegsUtil = 56, kRegsSoftmax = 224;           // 128*56 + 256*224 = 64512 = 384*168
+constexpr int kRegsUtil = 32, kRegsSoftmax = 112;           // 128*32 + 512*112 = 61440 = 640*96
 constexpr int kBars = 6 * kSlots + 2 * kQBufs * kSlots + 4 * kStages;
-constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages) * kTileBytes + kBars * 8 + 16;
+constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages) * kTileBytes + kBars * 8 + 16 + 2 * kSlots * 2 * kBM * 4;
 
 // One scheduling step of a CTA: query tile `qt` (and qt+1 when nslots == 2) of head h, batch b.
 struct Step { int b, h, qt, nslots; };
@@ -273,199 +325,255 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t* sK = sQ + kQBufs * kSlots * kTileBytes;      // [ST]
     uint8_t* sV = sK + ST * kTileBytes;                   // [ST]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * kTileBytes);
-    uint64_t* q_full = bars;                              // [kQBufs*kSlots]  TMA -> MMA : Q tile landed
-    uint64_t* q_empty = q_full + kQBufs * kSlots;         // [kQBufs*kSlots]  MMA -> TMA : last S = Q K^T of the step done
-    uint64_t* s_full = q_empty + kQBufs * kSlots;         // [kSlots]  MMA -> softmax   : S(n) complete
-    uint64_t* s_free = s_full + kSlots;                   // [kSlots]  softmax -> MMA   : S(n) copied to registers
-    uint64_t* p_full = s_free + kSlots;                   // [kSlots]  softmax -> MMA   : P(n) written to TMEM
-    uint64_t* pv_done = p_full + kSlots;                  // [kSlots]  MMA -> softmax   : O += P(n) V(n) complete
-    uint64_t* k_full = pv_done + kSlots;                  // [ST]
-    uint64_t* k_empty = k_full + ST;
-    uint64_t* v_full = k_empty + ST;
-    uint64_t* v_empty = v_full + ST;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + ST);
+    uint32_t sQ_a = smem_u32(sQ);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sQ_a));         // opaque: keep it in a register instead of re-deriving it (S2UR chain) at every use
+    const uint32_t sK_a = sQ_a + kQBufs * kSlots * kTileBytes, sV_a = sK_a + ST * kTileBytes;
+    const uint32_t q_full = sV_a + ST * kTileBytes;       // [kQBufs*kSlots]  TMA -> MMA : Q tile landed
+    const uint32_t q_empty = q_full + 8 * kQBufs * kSlots; // [kQBufs*kSlots]  MMA -> TMA : last S = Q K^T of the step issued
+    const uint32_t s_full = q_empty + 8 * kQBufs * kSlots; // [kSlots]  MMA -> softmax   : S(n) complete
+    const uint32_t s_free = s_full + 8 * kSlots;           // [kSlots]  softmax -> MMA   : S(n) copied to registers
+    const uint32_t p_full = s_free + 8 * kSlots;           // [kSlots]  softmax -> MMA   : P(n) written to TMEM
+    const uint32_t pv_done = p_full + 8 * kSlots;          // [kSlots]  MMA -> softmax   : O += P(n) V(n) complete
+    const uint32_t k_full = pv_done + 8 * kSlots;          // [ST]
+    const uint32_t k_empty = k_full + 8 * ST;
+    const uint32_t v_full = k_empty + 8 * ST;
+    const uint32_t v_empty = v_full + 8 * ST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars);
+    float* l_xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2 step parities][kSlots][2 halves][kBM] partial row sums
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const int T = (Nk + kBN - 1) / kBN;                   // K/V tiles per step
     const int last_valid = Nk - (T - 1) * kBN;            // valid kv rows of the last tile (1..128)
     const int tile_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
     const int tile_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
 
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kQBufs * kSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
-        for (int i = 0; i < ST; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], kSlots); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], kSlots); }
+    if (warp == kUtilWarp + 1 && lane == 0) {
+        for (int i = 0; i < kQBufs * kSlots; ++i) { mbar_init(q_full + 8u * (i), 1); mbar_init(q_empty + 8u * (i), 1); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(s_full + 8u * (i), 1); mbar_init(s_free + 8u * (i), 8); mbar_init(p_full + 8u * (i), 8); /* one arrival per softmax warp of the slot */ mbar_init(pv_done + 8u * (i), 1); }
+        for (int i = 0; i < ST; ++i) { mbar_init(k_full + 8u * (i), 1); mbar_init(k_empty + 8u * (i), 1); mbar_init(v_full + 8u * (i), 1); mbar_init(v_empty + 8u * (i), kSlots); }
         fence_barrier_init();
     }
-    if (warp == 0) {
+    if (warp == kUtilWarp) {
         if (lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
         __syncwarp();
-        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp < kFirstSoftmaxWarp) {
+    if (warp >= kUtilWarp) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegsUtil));
-        if (warp == 0) {
+        if (warp == kUtilWarp) {
             // ================================ TMA producer ================================
-            if (lane == 0) {
+            // the whole warp walks the schedule (uniform control flow); one elected lane issues
+            {
                 int it = tile_begin;
                 Step cur;
                 uint32_t sidx = 0, qbits = 0;                // per (buffer, slot) use parity
                 int st = 0;
                 uint32_t ph = 0;
+                TMX_TRACE_DECL(0, lane == 0)
                 while (next_step(it, tile_end, QT, H, pair, cur)) {
                     const int buf = (int)(sidx & 1u);
                     for (int w = 0; w < cur.nslots; ++w) {
                         const int qi = buf * kSlots + w;
-                        mbar_wait(&q_empty[qi], ((qbits >> qi) & 1u) ^ 1u);
+                        mbar_wait(q_empty + 8u * (qi), ((qbits >> qi) & 1u) ^ 1u);
                         qbits ^= 1u << qi;
-                        mbar_expect_tx(&q_full[qi], kTileBytes);
-                        tma_load_4d(sQ + qi * kTileBytes, &tm_q, &q_full[qi], 0, cur.h, (cur.qt + w) * kBM, cur.b);
+                        if (elect_one()) {
+                            mbar_expect_tx(q_full + 8u * (qi), kTileBytes);
+                            tma_load_4d(sQ_a + qi * kTileBytes, &tm_q, q_full + 8u * (qi), 0, cur.h, (cur.qt + w) * kBM, cur.b);
+                        }
                     }
                     for (int j = 0; j < T; ++j) {
-                        mbar_wait(&k_empty[st], ph ^ 1u);
-                        mbar_expect_tx(&k_full[st], kTileBytes);
-                        tma_load_4d(sK + st * kTileBytes, &tm_k, &k_full[st], 0, cur.h, j * kBN, cur.b);
-                        mbar_wait(&v_empty[st], ph ^ 1u);
-                        mbar_expect_tx(&v_full[st], kTileBytes);
-                        tma_load_4d(sV + st * kTileBytes, &tm_v, &v_full[st], 0, cur.h, j * kBN, cur.b);
+                        mbar_wait(k_empty + 8u * (st), ph ^ 1u);
+                        TMX_TRACE(0);
+                        if (elect_one()) {
+                            mbar_expect_tx(k_full + 8u * (st), kTileBytes);
+                            tma_load_4d(sK_a + st * kTileBytes, &tm_k, k_full + 8u * (st), 0, cur.h, j * kBN, cur.b);
+                        }
+                        mbar_wait(v_empty + 8u * (st), ph ^ 1u);
+                        TMX_TRACE(1);
+                        if (elect_one()) {
+                            mbar_expect_tx(v_full + 8u * (st), kTileBytes);
+                            tma_load_4d(sV_a + st * kTileBytes, &tm_v, v_full + 8u * (st), 0, cur.h, j * kBN, cur.b);
+                        }
                         if (++st == ST) { st = 0; ph ^= 1u; }
                     }
                     ++sidx;
                 }
             }
-        } else if (warp <= kSlots) {
-            // ================================ MMA issuer of slot w ========================
-            // Walks the CTA's K/V stream tile by tile.  For every tile it first issues S = Q K^T of the
-            // NEXT tile in the stream (possibly the first tile of the next step: cross-step prefetch),
-            // then O += P V of the current one.  In a step where this slot has no query tile it only
-            // releases the K/V stages on the slot's behalf.
-            if (lane == 0) {
-                const int w = warp - 1;
-                constexpr uint32_t idesc_qk = make_idesc(BF16, BF16, kBM, kBN, false);
-                constexpr uint32_t idesc_pv = make_idesc(BF16, BF16, kBM, kD, true);
-                const uint32_t t_s = tmem_base + w * 256, t_o = t_s + 128, t_p = t_s + 192;
-                const int last_ksteps = (last_valid + 15) >> 4;
-                auto issue_qk = [&](int qi, int stage) {
-                    const uint32_t a0 = smem_u32(sQ + qi * kTileBytes);
-                    const uint32_t b0 = smem_u32(sK + stage * kTileBytes);
-#pragma unroll
-                    for (int k = 0; k < kD / 16; ++k)                    // 4 x (K = 16): +32 B inside the 128 B swizzle row
-                        umma_ss(t_s, make_sw128_desc(a0 + k * 32, 16, 1024), make_sw128_desc(b0 + k * 32, 16, 1024), idesc_qk, k > 0);
-                };
-                auto issue_pv = [&](int stage, bool acc, int ksteps) {
-                    const uint32_t b0 = smem_u32(sV + stage * kTileBytes);
-                    for (int k = 0; k < ksteps; ++k)                     // (K = 16 kv rows): +2048 B in V, +8 columns in P
-                        umma_ts(t_o, t_p + k * 8, make_sw128_desc(b0 + k * 2048, 16, 1024), idesc_pv, (acc || k > 0) ? 1u : 0u);
-                };
-                int it = tile_begin;
-                Step cur, nxt;
-                bool has_cur = next_step(it, tile_end, QT, H, pair, cur);
-                uint32_t nS = 0, nPV = 0, sidx = 0, qbits = 0;   // qbits: per Q buffer use parity of this slot
-                int st = 0;                     // stage / phase of the CURRENT tile of the stream
-                uint32_t ph = 0;
-                if (has_cur) {                  // prologue: S of the very first tile
-                    mbar_wait(&k_full[0], 0);
-                    if (w < cur.nslots) {
-                        mbar_wait(&q_full[w], 0);
-                        qbits ^= 1u;
-                        tc_fence_after();
-                        issue_qk(w, 0);
-                        umma_commit(&s_full[w]);
-                        umma_commit(&k_empty[0]);
-                        ++nS;
-                        if (T == 1) umma_commit(&q_empty[w]);
-                    } else {
-                        mbar_arrive(&k_empty[0]);
-                    }
+        } else if (warp == kUtilWarp + 1) {
+            // ================================ S = Q K^T issuer (both slots) ===============
+            // Walks the CTA's K/V stream tile by tile and, per tile, issues S = Q K^T for every active
+            // slot as soon as the slot's S buffer is free.  It is not tied to the P V issue, so it runs
+            // ahead of the softmax as far as the barriers allow (also across steps).
+            constexpr uint32_t idesc_qk = make_idesc(BF16, BF16, kBM, kBN, false);
+            const uint32_t q_lo0 = desc_lo(sQ_a), k_lo0 = desc_lo(sK_a);
+            int it = tile_begin;
+            Step cur;
+            uint32_t nS0 = 0, nS1 = 0, sidx = 0, qbits = 0;   // qbits: per (buffer, slot) use parity
+            int st = 0;
+            uint32_t ph = 0;
+            TMX_TRACE_DECL(1, lane == 0)
+            while (next_step(it, tile_end, QT, H, pair, cur)) {
+                const int buf = (int)(sidx & 1u);
+                const bool two = cur.nslots == 2;
+                {
+                    mbar_wait(q_full + 8u * (buf * kSlots), (qbits >> (buf * kSlots)) & 1u);
+                    qbits ^= 1u << (buf * kSlots);
+                    if (two) { mbar_wait(q_full + 8u * (buf * kSlots + 1), (qbits >> (buf * kSlots + 1)) & 1u); qbits ^= 1u << (buf * kSlots + 1); }
                 }
-                while (has_cur) {
-                    const bool has_nxt = next_step(it, tile_end, QT, H, pair, nxt);
-                    const bool act = w < cur.nslots;
-                    const int buf = (int)(sidx & 1u);
-                    for (int j = 0; j < T; ++j) {
-                        const bool last = (j == T - 1);
-                        if (!last || has_nxt) {
-                            int sn = st + 1;
-                            uint32_t pn = ph;
-                            if (sn == ST) { sn = 0; pn ^= 1u; }
-                            const bool nact = last ? (w < nxt.nslots) : act;
-                            mbar_wait(&k_full[sn], pn);
-                            if (nact) {
-                                const int nb = last ? (buf ^ 1) : buf;
-                                const int qi = nb * kSlots + w;
-                                if (last) { mbar_wait(&q_full[qi], (qbits >> nb) & 1u); qbits ^= 1u << nb; }
-                                if (nS > 0) mbar_wait(&s_free[w], (nS - 1u) & 1u);
-                                tc_fence_after();
-                                issue_qk(qi, sn);
-                                umma_commit(&s_full[w]);
-                                umma_commit(&k_empty[sn]);
-                                ++nS;
-                                const bool last_qk_of_step = last ? (T == 1) : (j + 1 == T - 1);
-                                if (last_qk_of_step) umma_commit(&q_empty[qi]);
-                            } else {
-                                mbar_arrive(&k_empty[sn]);
-                            }
-                        }
-                        mbar_wait(&v_full[st], ph);
-                        if (act) {
-                            mbar_wait(&p_full[w], nPV & 1u);
-                            tc_fence_after();
-                            issue_pv(st, j > 0, last ? last_ksteps : kBN / 16);
-                            umma_commit(&pv_done[w]);
-                            umma_commit(&v_empty[st]);
-                            ++nPV;
-                        } else {
-                            mbar_arrive(&v_empty[st]);
-                        }
-                        if (++st == ST) { st = 0; ph ^= 1u; }
+                const uint32_t a_lo0 = q_lo0 + (uint32_t)(buf * kSlots) * (kTileBytes >> 4);
+                for (int j = 0; j < T; ++j) {
+                    const uint32_t b_lo = k_lo0 + (uint32_t)st * (kTileBytes >> 4);
+                    mbar_wait(k_full + 8u * (st), ph);
+                    TMX_TRACE(10);
+                    if (nS0 > 0) mbar_wait(s_free + 8u * (0), (nS0 - 1u) & 1u);
+                    TMX_TRACE(11);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        umma_ss_lo<false>(tmem_base, a_lo0, b_lo, idesc_qk);           // 4 x (K = 16): +32 B inside the 128 B swizzle row
+                        umma_ss_lo<true>(tmem_base, a_lo0 + 2, b_lo + 2, idesc_qk);
+                        umma_ss_lo<true>(tmem_base, a_lo0 + 4, b_lo + 4, idesc_qk);
+                        umma_ss_lo<true>(tmem_base, a_lo0 + 6, b_lo + 6, idesc_qk);
+                        umma_commit(s_full + 8u * (0));
+                        if (!two) umma_commit(k_empty + 8u * (st));
                     }
-                    cur = nxt;
-                    has_cur = has_nxt;
-                    ++sidx;
+                    TMX_TRACE(12);
+                    ++nS0;
+                    if (two) {
+                        if (nS1 > 0) mbar_wait(s_free + 8u * (1), (nS1 - 1u) & 1u);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_lo1 = a_lo0 + (kTileBytes >> 4);
+                            umma_ss_lo<false>(tmem_base + 256, a_lo1, b_lo, idesc_qk);
+                            umma_ss_lo<true>(tmem_base + 256, a_lo1 + 2, b_lo + 2, idesc_qk);
+                            umma_ss_lo<true>(tmem_base + 256, a_lo1 + 4, b_lo + 4, idesc_qk);
+                            umma_ss_lo<true>(tmem_base + 256, a_lo1 + 6, b_lo + 6, idesc_qk);
+                            umma_commit(s_full + 8u * (1));
+                            umma_commit(k_empty + 8u * (st));
+                        }
+                        ++nS1;
+                    }
+                    if (++st == ST) { st = 0; ph ^= 1u; }
+                }
+                if (elect_one()) {                         // every S = Q K^T of this step has been issued: Q buffers may be refilled
+                    umma_commit(q_empty + 8u * (buf * kSlots));
+                    if (two) umma_commit(q_empty + 8u * (buf * kSlots + 1));
+                }
+                ++sidx;
+            }
+        } else {
+            // ================================ O += P V issuer of slot w ===================
+            const int w = warp - kUtilWarp - 2;
+            constexpr uint32_t idesc_pv = make_idesc(BF16, BF16, kBM, kD, true);
+            const uint32_t t_o = tmem_base + w * 256 + 128, t_p = t_o + 64;
+            const int last_ksteps = (last_valid + 15) >> 4;
+            const uint32_t v_lo0 = desc_lo(sV_a);
+            int it = tile_begin;
+            Step cur;
+            uint32_t nPV = 0;
+            int st = 0;
+            uint32_t ph = 0;
+            TMX_TRACE_DECL(3, w == 0 && lane == 0)
+            while (next_step(it, tile_end, QT, H, pair, cur)) {
+                const bool act = w < cur.nslots;
+                for (int j = 0; j < T; ++j) {
+                    const uint32_t b_lo = v_lo0 + (uint32_t)st * (kTileBytes >> 4);
+                    mbar_wait(v_full + 8u * (st), ph);
+                    TMX_TRACE(13);
+                    if (act) {
+                        mbar_wait(p_full + 8u * (w), nPV & 1u);
+                        TMX_TRACE(14);
+                        tc_fence_after();
+                        if (elect_one()) {                                 // (K = 16 kv rows): +2048 B in V, +8 columns in P
+                            if (j < T - 1 || last_ksteps == kBN / 16) {
+                                umma_ts_lo(t_o, t_p, b_lo, idesc_pv, j > 0 ? 1u : 0u);
+#pragma unroll
+                                for (int k = 1; k < kBN / 16; ++k) umma_ts_lo(t_o, t_p + k * 8, b_lo + k * 128, idesc_pv, 1u);
+                            } else {
+                                for (int k = 0; k < last_ksteps; ++k) umma_ts_lo(t_o, t_p + k * 8, b_lo + k * 128, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                            }
+                            umma_commit(pv_done + 8u * (w));
+                            umma_commit(v_empty + 8u * (st));
+                        }
+                        TMX_TRACE(15);
+                        ++nPV;
+                    } else if (elect_one()) {
+                        mbar_arrive(v_empty + 8u * (st));
+                    }
+                    if (++st == ST) { st = 0; ph ^= 1u; }
                 }
             }
         }
     } else {
         // ================================ softmax / correction / epilogue ==============
+        // Two threads per query row (TMEM lane): `half` 0 exponentiates columns [0,64), half 1 columns
+        // [64,128) of every S tile.  Both read the whole row for the running max (bit-identical in the
+        // two threads, so they take the same lazy-rescale decisions without talking to each other);
+        // each keeps a partial row sum and owns 32 of the 64 O columns; the sums meet once per step.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegsSoftmax));
-        const int w = (warp - kFirstSoftmaxWarp) >> 2;       // slot handled by this warp group
+        const int sw = warp;
+        const int w = (sw >> 2) & 1;                         // slot handled by this warp
+        const int half = sw >> 3;                            // column half of the S tile
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;                 // row in the tile == TMEM lane
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + w * 256;
+        const uint32_t t_own = t_row + half * 64, t_other = t_row + (half ^ 1) * 64;
         const uint64_t sc2 = pk2(scale_log2, scale_log2);
-        const int last_chunks = (last_valid + 31) >> 5;
+        int last_chunks = (last_valid - half * 64 + 31) >> 5;            // own chunks of the last K/V tile
+        last_chunks = last_chunks < 0 ? 0 : (last_chunks > 2 ? 2 : last_chunks);
         uint32_t n = 0;                                      // tiles processed by this slot (barrier phases)
+        uint32_t nstep = 0;
+        TMX_TRACE_DECL(2, sw == 0 && lane == 0)
         int it = tile_begin;
         Step cur;
         while (next_step(it, tile_end, QT, H, pair, cur)) {
             if (w >= cur.nslots) continue;
             float m_ref = -INFINITY;                         // running reference max, log2 domain (scaled)
-            float l_sum = 0.f;
+            float l_sum = 0.f;                               // partial row sum over this thread's columns
             for (int j = 0; j < T; ++j, ++n) {
-                mbar_wait(&s_full[w], n & 1u);
+                const bool last = (j == T - 1);
+                const bool partial = last && last_valid < kBN;
+                mbar_wait(s_full + 8u * (w), n & 1u);
+                TMX_TRACE(20);
                 tc_fence_after();
-                uint32_t s[128];
-                tmem_ld32(t_row + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-                tmem_ld32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-                tmem_ld32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
-                tmem_ld32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+                uint32_t s[64];
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#ifndef TMX_ATTN_EXPERIMENT_NOMAX
+                // the other half of the row: only its maximum is needed
+                tmem_ld32(t_other + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                tmem_ld32(t_other + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+                tc_wait_ld();
+                if (partial) {
+                    const int v = last_valid - (half ^ 1) * 64;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) if (c >= v) s[c] = 0xff800000u;   // -inf
+                }
+#pragma unroll
+                for (int c = 0; c < 64; c += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[c])); mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+                }
+#endif
+                // this thread's half
+                tmem_ld32(t_own + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                tmem_ld32(t_own + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
                 tc_wait_ld();
                 tc_fence_before();
-                mbar_arrive(&s_free[w]);                                   // S(n) is in registers: the MMA warp may overwrite it
-                const bool last = (j == T - 1);
-                const int chunks = last ? last_chunks : 4;
-                if (last && last_valid < kBN) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free + 8u * (w));                    // S(n) is consumed: the MMA warp may overwrite it
+                TMX_TRACE(21);
+                if (partial) {
+                    const int v = last_valid - half * 64;
 #pragma unroll
-                    for (int c = 0; c < 128; ++c) if (c >= last_valid) s[c] = 0xff800000u;   // -inf
+                    for (int c = 0; c < 64; ++c) if (c >= v) s[c] = 0xff800000u;   // -inf
                 }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 128; c += 4) {
+                for (int c = 0; c < 64; c += 4) {
                     mx0 = fmaxf(mx0, __uint_as_float(s[c])); mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
                     mx2 = fmaxf(mx2, __uint_as_float(s[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
                 }
@@ -475,26 +583,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const float m_new = bump ? m_tile : m_ref;
                 bool pv_waited = false;
                 if (j > 0 && __any_sync(0xffffffffu, bump)) {            // warp-uniform: tcgen05.ld/st are warp-collective
-                    mbar_wait(&pv_done[w], (n - 1u) & 1u);               // O must hold every P V issued so far
+                    mbar_wait(pv_done + 8u * (w), (n - 1u) & 1u);               // O must hold every P V issued so far
                     tc_fence_after();
                     pv_waited = true;
                     const float alpha = bump ? ex2(m_ref - m_new) : 1.f;
                     l_sum *= alpha;
+                    uint32_t o[32];
+                    tmem_ld32(t_row + 128 + half * 32, o);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t o[32];
-                        tmem_ld32(t_row + 128 + half * 32, o);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-                        tmem_st32(t_row + 128 + half * 32, o);
-                    }
+                    for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                    tmem_st32(t_row + 128 + half * 32, o);
                 }
                 m_ref = m_new;
+                const int chunks = last ? last_chunks : 2;
                 const uint64_t nm2 = pk2(-m_new, -m_new);
                 uint64_t sum_a = pk2(0.f, 0.f), sum_b = pk2(0.f, 0.f);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     if (q < chunks) {
                         uint32_t p[16];
 #pragma unroll
@@ -506,17 +612,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                             } else {
                                 float x0, x1;
                                 upk2(x2, x0, x1);
+#ifdef TMX_ATTN_EXPERIMENT_NOEXP
+                                e0 = x0; e1 = x1;
+#else
                                 e0 = ex2(x0);
                                 e1 = ex2(x1);
+#endif
                             }
                             if (c & 1) sum_b = fadd2(sum_b, pk2(e0, e1)); else sum_a = fadd2(sum_a, pk2(e0, e1));
                             p[c] = pack2<BF16>(e0, e1);
                         }
-                        if (q == 0 && j > 0 && !pv_waited) {               // P(n-1) must have been consumed before it is overwritten
-                            mbar_wait(&pv_done[w], (n - 1u) & 1u);
+                        if (q == 0) TMX_TRACE(22);
+                        if (!pv_waited && j > 0) {                         // P(n-1) must have been consumed before it is overwritten
+                            mbar_wait(pv_done + 8u * (w), (n - 1u) & 1u);
                             tc_fence_after();
+                            pv_waited = true;
                         }
-                        tmem_st16(t_row + 192 + q * 16, p);
+                        if (q == 0) TMX_TRACE(23);
+                        tmem_st16(t_row + 192 + half * 32 + q * 16, p);
                     }
                 }
                 {
@@ -525,20 +638,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     upk2(sum_b, b0, b1);
                     l_sum += (a0 + a1) + (b0 + b1);
                 }
+                TMX_TRACE(24);
                 tc_wait_st();
                 tc_fence_before();
-                mbar_arrive(&p_full[w]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full + 8u * (w));
+                TMX_TRACE(25);
             }
 
-            // epilogue: O / l -> global (row-contiguous 128 B per thread)
-            mbar_wait(&pv_done[w], (n - 1u) & 1u);
+            // epilogue: the two halves exchange their partial sums, then O / l -> global (64 B of the row per thread)
+            float* lx = l_xchg + ((nstep & 1u) * kSlots + w) * 2 * kBM;
+            lx[half * kBM + row] = l_sum;
+            asm volatile("bar.sync %0, 256;" :: "r"(1 + w) : "memory");
+            const float inv_l = 1.f / (l_sum + lx[(half ^ 1) * kBM + row]);
+            ++nstep;
+            mbar_wait(pv_done + 8u * (w), (n - 1u) & 1u);
             tc_fence_after();
-            const float inv_l = 1.f / l_sum;
             const int q_row = (cur.qt + w) * kBM + row;
             uint8_t* dst = reinterpret_cast<uint8_t*>(o_ptr) +
-                           (((size_t)cur.b * Nq + (size_t)q_row) * (size_t)o_stride_n + (size_t)cur.h * kD) * 2;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+                           (((size_t)cur.b * Nq + (size_t)q_row) * (size_t)o_stride_n + (size_t)cur.h * kD + half * 32) * 2;
+            {
                 uint32_t o[32];
                 tmem_ld32(t_row + 128 + half * 32, o);
                 tc_wait_ld();
@@ -550,7 +669,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
                         v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
                         v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-                        *reinterpret_cast<uint4*>(dst + (half * 32 + c) * 2) = v;
+                        *reinterpret_cast<uint4*>(dst + c * 2) = v;
                     }
                 }
             }
@@ -560,7 +679,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kUtilWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -603,6 +722,12 @@ static int g_variant = 0;   // test hook: 0 / 2 = pair query tiles (default), 1 
 }  // namespace tmx
 
 using namespace tmx;
+
+#ifdef TMX_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int tmx_attn_debug_trace(long long* host, int role) {
+    return check_cuda(cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * kTraceLen, sizeof(long long) * kTraceLen * role), "trace copy");
+}
+#endif
 
 extern "C" int tmx_attn_set_variant(int nq) {
     TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1 or 2");
