@@ -47,7 +47,7 @@ SHAPES = [  # B, H, Nq, Nk
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("nq", [1, 2])
+@pytest.mark.parametrize("nq", [1, 2, 11, 12])   # 1: lone query tiles, 2: paired; 11 / 12: one / two softmax threads per row
 @pytest.mark.parametrize("shape", SHAPES)
 def test_attention_matches_oracle(shape, nq, dtype):
     o = ops()

@@ -62,8 +62,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--attn-variant", type=int, default=0, help="tmx_attn_set_variant() value (11 / 12 = one / two softmax threads per row)")
     ap.add_argument("--shapes", default="", help="comma-separated substrings; only shapes whose tag contains one are run (profiling aid)")
     args = ap.parse_args()
+    if args.attn_variant:
+        from tweediemix_b200 import _lib
+        build.build()
+        assert _lib.load().tmx_attn_set_variant(args.attn_variant) == 0
     only = set(args.only.split(",")) if args.only else None
     build.build()
     hbm, tf = peaks()
