@@ -148,7 +148,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": ref.threads, "kind": "port", "sample": ref.sample_description(),
                              "seconds_per_sample_forward": sec},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -363,14 +363,36 @@ def run_ours(args):
                 "gpu_launches": launches, "gpu_launches_by_kernel": {k: v for k, v in ops.LAUNCHES.items()},
                 "roofline": roof, "roofline_other": others, "fused_step_tmx_kernel_ms": step_kernel_ms,
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout: send everything libraries print to fd 1 (NCCL's version banner, ...) to
+    stderr and keep a private duplicate of the real stdout for the result line."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _protect_stdout()
     args = parse()
     if args.impl == "reference":
         return run_reference(args)

@@ -6,11 +6,16 @@ package; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 the timed CPU baseline, never as the shipped path.
 
 Parity pinning:
-  * the reference ships no tests and no golden vectors, and its
-    sampler cannot be imported here (diffusers/xformers absent), so the
-    sampler-level restatement (``step_math``, ``sampler_ref``) is pinned only
-    by the schedule table in SURVEY App. C and by hand-derived known answers:
-    **parity unpinned** for those two modules;
+  * the reference ships no tests and no golden vectors.  Its sampler
+    files do not import as they are (diffusers / sentence_transformers absent), but
+    with those imports stubbed the reference's UNMODIFIED ``Tweediemix.init_fusion``,
+    ``alpha`` and ``denoise_step`` run on CPU: ``tests/golden/make_golden_sampler.py``
+    records their latents step by step (custom 5-step config 1, LoRA 10-step with
+    ``t_stop``, one step per phase) and ``tests/test_oracle_vs_reference_sampler.py``
+    holds ``sampler_ref`` / ``step_math`` / ``schedule`` / ``masks_ref`` to them at
+    2e-5 relative: **pinned**;
+  * only ``unet_ref`` (the diffusers U-Net body, [D]) remains **parity unpinned**:
+    diffusers cannot be installed here, and the reference treats it as a black box;
   * the hook restatement (``hooks_ref``) IS pinned: the reference's own
     ``fusion_generation/utils_custom.py`` and ``utils_lora.py`` import and run
     in the build container, and ``tests/golden/make_golden.py`` records their

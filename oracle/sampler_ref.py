@@ -8,7 +8,9 @@ outside the hot path: text embeddings and region masks are inputs here (north_st
 precomputed), so the jump loop ``:431-455`` — which never alters the returned latent — is run
 only when ``run_jump=True`` (to reproduce the forward-call count).
 
-PARITY UNPINNED at this level (no reference tests; sampler not importable here).
+Pinned against the reference's own ``init_fusion`` / ``alpha`` / ``denoise_step`` run unmodified on
+CPU (``tests/golden/make_golden_sampler.py`` -> ``tests/golden/sampler_*.pt``, ``step_math_ref.pt``;
+checked by ``tests/test_oracle_vs_reference_sampler.py`` at 2e-5 relative per step).
 """
 from __future__ import annotations
 

@@ -9,9 +9,10 @@ reproduces the reference's mixed-precision rounding, and with fp32 ``eps`` gives
 the fp32 ground truth.
 
 Reference: ``fusion_generation/fusion_sampling.py`` (line numbers per function).
-PARITY UNPINNED at this level — the reference has no tests/golden vectors for
-the sampler and cannot be imported here (diffusers absent); pinned only by
-hand-derived known answers in ``tests/test_oracle_step_math.py``.
+Pinned: the reference's unmodified ``denoise_step`` is run on CPU by
+``tests/golden/make_golden_sampler.py`` (third-party imports stubbed) and
+``tests/test_oracle_vs_reference_sampler.py`` compares this module to its latents in
+all four phases; ``tests/test_oracle_step_math.py`` adds hand-derived known answers.
 """
 from __future__ import annotations
 
