@@ -117,10 +117,12 @@ TMX_API int tmx_blend_finish_fwd(const float* x, const float* acc, const float* 
  *
  * x, y      : dtype [N, C, HW] (TMX_NCHW) or [N, HW, C] (TMX_NHWC); y may alias x
  * gamma/beta: fp32 [C];  add: fp32 [N, C] or NULL
- * workspace : tmx_groupnorm_workspace_bytes(N, C, HW, G, layout) bytes, 16-byte aligned; its first 4 KiB
- *             (per-row completion tickets) must be ZERO before the first launch — the kernels leave
- *             them zero again, so one memset at allocation is enough; N <= 1024;
- *             one launch at a time per workspace (launches on the same stream are fine)
+ * workspace : tmx_groupnorm_workspace_bytes(N, C, HW, G, layout) bytes, 16-byte aligned; its first 8 KiB
+ *             (per-row arrival counters, returned to zero by every launch, and per-row barrier generation
+ *             words, monotonic) must be ZERO before the first launch — one memset at allocation is enough;
+ *             N <= 1024; one launch at a time per workspace (launches on the same stream are fine)
+ * NHWC 16-bit activations that fit in one wave of shared memory (N * floor(#SM/N) CTAs x <= 200 KB) run as ONE
+ * cooperative launch that reads x once and writes y once; larger ones as two launches (stats, apply).
  * Statistics in fp32 (Chan/Welford merge, deterministic), one rounding on store.
  * Requires C % G == 0, C % 8 == 0 (NHWC) or HW*(C/G) % 8 == 0 (NCHW).
  * Algorithmic bytes: 2 * N*C*HW * sizeof(dtype).
@@ -129,6 +131,12 @@ TMX_API size_t tmx_groupnorm_workspace_bytes(int N, int C, int HW, int G, int la
 TMX_API int    tmx_groupnorm_fwd(const void* x, const float* gamma, const float* beta, const float* add,
                          void* y, void* workspace, int N, int C, int HW, int G, float eps,
                          int act, int layout, int dtype, void* stream);
+
+/* Tuning / test hook: 0 = fused single-launch path when applicable (default), 1 = always two launches,
+ * 2 = fused kernel through a plain (non-cooperative) launch. */
+TMX_API int tmx_groupnorm_set_variant(int v);
+/* Number of kernels tmx_groupnorm_fwd launches for this shape (1 fused, 2 stats + apply): launch accounting. */
+TMX_API int tmx_groupnorm_launches(int N, int C, int HW, int layout, int dtype);
 
 /* k6 — residual add:  y = (a + b) * inv_scale    ([D] ResnetBlock2D tail, output_scale_factor;
  * also the three residual adds of BasicTransformerBlock).  n elements, n % 8 == 0; y may alias. */

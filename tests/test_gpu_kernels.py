@@ -146,12 +146,24 @@ def _gn_ref(x, gamma, beta, groups, eps, add, silu):
     return F.silu(y) if silu else y
 
 
+@pytest.fixture(params=[0, 1], ids=["fused", "two_pass"])
+def gn_variant(request):
+    """0: the single cooperative launch (slab kept in shared memory) where it applies; 1: stats + apply launches."""
+    from tweediemix_b200 import _lib
+    ops()
+    _lib.load().tmx_groupnorm_set_variant(request.param)
+    yield request.param
+    _lib.load().tmx_groupnorm_set_variant(0)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("layout", ["nhwc", "nchw"])
-@pytest.mark.parametrize("shape", GN_SHAPES)
-def test_groupnorm_matches_fp32_reference(dtype, layout, shape):
+@pytest.mark.parametrize("shape", GN_SHAPES + [(4, 640, 64, 64), (4, 1280, 32, 32)])
+def test_groupnorm_matches_fp32_reference(dtype, layout, shape, gn_variant):
     o = ops()
     N, C, H, W = shape
+    if gn_variant == 1 and (layout == "nchw" or dtype == torch.float32):
+        pytest.skip("variant only changes the NHWC 16-bit path")
     if layout == "nchw" and (H * W) % 8:
         pytest.skip("NCHW kernel requires HW % 8 == 0 (checked in test_groupnorm_errors)")
     g = torch.Generator().manual_seed(C + H)
@@ -173,7 +185,7 @@ def test_groupnorm_matches_fp32_reference(dtype, layout, shape):
                                        rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
 
 
-def test_groupnorm_large_mean_is_stable_and_inplace():
+def test_groupnorm_large_mean_is_stable_and_inplace(gn_variant):
     """|mean| >> std: the pivot-shifted sums must not cancel catastrophically."""
     o = ops()
     g = torch.Generator().manual_seed(5)
@@ -183,6 +195,13 @@ def test_groupnorm_large_mean_is_stable_and_inplace():
     xc = x.cuda().contiguous(memory_format=torch.channels_last)
     o.group_norm(xc, gamma.cuda(), beta.cuda(), 32, 1e-5, out=xc)
     torch.testing.assert_close(xc.cpu(), want, rtol=2e-3, atol=2e-3)
+    # 16-bit, in place, launched back to back (the barrier words in the workspace are reused by every launch)
+    xb = (torch.randn(4, 1280, 32, 32, generator=g) * 0.5 + 3.0).to(torch.bfloat16)
+    wantb = _gn_ref(xb, torch.ones(1280), torch.zeros(1280), 32, 1e-5, None, True)
+    for _ in range(3):
+        xc = xb.cuda().contiguous(memory_format=torch.channels_last)
+        o.group_norm(xc, torch.ones(1280).cuda(), torch.zeros(1280).cuda(), 32, 1e-5, silu=True, out=xc)
+        torch.testing.assert_close(xc.cpu().float(), wantb.to(torch.bfloat16).float(), rtol=2 ** -7, atol=2e-3)
 
 
 def test_groupnorm_errors():

@@ -63,8 +63,13 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--attn-variant", type=int, default=0, help="tmx_attn_set_variant() value (11 / 12 = one / two softmax threads per row)")
+    ap.add_argument("--gn-variant", type=int, default=0, help="tmx_groupnorm_set_variant(): 0 fused cooperative, 1 two launches, 2 fused plain launch")
     ap.add_argument("--shapes", default="", help="comma-separated substrings; only shapes whose tag contains one are run (profiling aid)")
     args = ap.parse_args()
+    if args.gn_variant:
+        from tweediemix_b200 import _lib
+        build.build()
+        assert _lib.load().tmx_groupnorm_set_variant(args.gn_variant) == 0
     if args.attn_variant:
         from tweediemix_b200 import _lib
         build.build()

@@ -1,6 +1,11 @@
 // k4 / k5 — GroupNorm (+ per-(n,c) additive bias before the norm, + SiLU), NHWC and NCHW.
 //
-// HBM-bound.  Two launches: `stats` reads x once (128-bit coalesced loads, 4 rows in flight per
+// HBM-bound.  Activations that fit in the shared memory of one wave (N * floor(#SM / N) CTAs, one per SM,
+// <= ~190 KB each: every 32x32 and 64x64 site of the SDXL U-Net at batch 4) take the FUSED path: one
+// cooperative launch loads the CTA's contiguous NHWC slab once, keeps it in shared memory while the CTAs
+// of a batch row meet at a sense-reversing barrier in global memory (the last arriver folds the partial
+// sums), then normalises out of shared memory: x is read once and y written once (2 * s * elems, the
+// algorithmic minimum).  Larger activations take two launches: `stats` reads x once (128-bit coalesced loads, 4 rows in flight per
 // thread) and writes per-CTA shifted partial sums; `apply` re-reads x — from the 126 MB L2 for
 // every SDXL activation that fits — folds the statistics, gamma, beta and the additive bias into
 // one fma per element, applies SiLU and stores once.  Statistics are fp32 sums of (x - pivot)
@@ -40,6 +45,46 @@ template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return _
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 __device__ __forceinline__ float silu(float y) { return __fdividef(y, 1.f + __expf(-y)); }
+// y * sigmoid(y) = h + h * tanh(h), h = y / 2: ONE MUFU op per element (tanh.approx, rel. error ~2^-11) instead of
+// two (ex2 + rcp).  The apply pass of a 16-bit activation is MUFU-bound otherwise; the error is below the output rounding.
+__device__ __forceinline__ float silu_fast(float y) {
+    const float h = 0.5f * y;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+template <typename T> __device__ __forceinline__ float silu_for(float y) { return sizeof(T) == 2 ? silu_fast(y) : silu(y); }
+
+
+// Per-CTA reduction of the per-thread channel sums (S, SS)[8] to per-group sums, deterministic order.
+// sh: [8][RY][CV] float2 (conflict-free: consecutive threads write consecutive words), then [C] float2 channel totals.
+// Stage A: the first CV threads add the RY row lanes of their 8 channels; stage B: one warp per group adds its cpg
+// channels (lanes stride the channels: no integer division anywhere).  Returns with the group sum valid in lane 0
+// through the callback `emit(g, s, ss)`.
+template <typename F>
+__device__ __forceinline__ void gn_cta_group_sums(float2* sh, const float (&S)[8], const float (&SS)[8],
+                                                  int C, int CV, int RY, int G, int cpg, int tx, int ty, F emit) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[((size_t)j * RY + ty) * CV + tx] = make_float2(S[j], SS[j]);
+    __syncthreads();
+    float2* ch = sh + (size_t)8 * RY * CV;                // [C] channel totals
+    if (threadIdx.x < CV) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = 0.f, ss = 0.f;
+            for (int t = 0; t < RY; ++t) { const float2 v = sh[((size_t)j * RY + t) * CV + threadIdx.x]; s += v.x; ss += v.y; }
+            ch[threadIdx.x * 8 + j] = make_float2(s, ss);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < G; g += nwarps) {
+        float s = 0.f, ss = 0.f;
+        for (int i = lane; i < cpg; i += 32) { const float2 v = ch[g * cpg + i]; s += v.x; ss += v.y; }
+        s = warp_sum(s); ss = warp_sum(ss);
+        if (lane == 0) emit(g, s, ss);
+    }
+}
 
 // ------------------------------------------------------------------------------------------ NHWC
 // grid (P, N); block = CV * RY threads (CV = C/8 channel vectors, RY row lanes), 2 CTAs per SM.
@@ -54,7 +99,7 @@ __global__ void __launch_bounds__(kGnMaxThreads, 2)
 gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __restrict__ part,
               float2* __restrict__ stat, unsigned int* __restrict__ tickets,
               int C, int HW, int G, int rows_per_cta, float eps) {
-    extern __shared__ float2 sh[];                      // [RY][C] partials, then reused
+    extern __shared__ float2 sh[];                      // [8][RY][CV] partials + [C] channel totals (gn_cta_group_sums)
     __shared__ float s_piv[64];
     __shared__ unsigned int s_ticket;
     const int CV = C >> 3, RY = blockDim.x / CV, cpg = C / G;
@@ -114,20 +159,9 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d0 = f0[j] - kk[j]; S[j] += d0; SS[j] = fmaf(d0, d0, SS[j]); }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sh[(size_t)ty * C + tx * 8 + j] = make_float2(S[j], SS[j]);
-    __syncthreads();
-    // one warp per group, fixed summation order
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int g = warp; g < G; g += nwarps) {
-        float s = 0.f, ss = 0.f;
-        for (int i = lane; i < RY * cpg; i += 32) {
-            const float2 v = sh[(size_t)(i / cpg) * C + g * cpg + (i % cpg)];
-            s += v.x; ss += v.y;
-        }
-        s = warp_sum(s); ss = warp_sum(ss);
-        if (lane == 0) part[((size_t)n * G + g) * P + blockIdx.x] = make_float2(s, ss);
-    }
+    gn_cta_group_sums(sh, S, SS, C, CV, RY, G, cpg, tx, ty,
+                      [&](int g, float s, float ss) { part[((size_t)n * G + g) * P + blockIdx.x] = make_float2(s, ss); });
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // blockDim.x is a multiple of 32 (plan_nhwc)
     // ---- last CTA of this row finalises the statistics
     __threadfence();
     __syncthreads();
@@ -195,7 +229,7 @@ gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float v = fmaf(f[j], a[j], b[j]);
-                        f[j] = act ? silu(v) : v;
+                        f[j] = act ? silu_for<T>(v) : v;
                     }
                     st_stream(ycol + (size_t)(r + u * RY) * C, pack8<T>(f));
                 }
@@ -212,9 +246,176 @@ gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float v = fmaf(f[j], a[j], b[j]);
-            f[j] = act ? silu(v) : v;
+            f[j] = act ? silu_for<T>(v) : v;
         }
         V8<T>::store(ycol + (size_t)r * C, f);
+    }
+}
+
+
+// --------------------------------------------------------------------------------- NHWC, fused
+// grid (P, N) <= #SM CTAs, launched cooperatively (all co-resident); block = CV * RY threads as above.
+// smem: [rows_per_cta][CV] uint4 slab | [RY][C] float2 reduction scratch.
+// sync[n] = arrival counter of batch row n (left at zero), sync[1024 + n] = barrier generation (zero-initialised once).
+template <typename T>
+__global__ void __launch_bounds__(kGnMaxThreads, 1)
+gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ add, float2* __restrict__ part, float2* __restrict__ stat,
+              unsigned int* __restrict__ sync, T* __restrict__ y,
+              int C, int HW, int G, int rows_per_cta, float eps, int act) {
+    extern __shared__ uint4 gn_smem[];
+    __shared__ float s_piv[64];
+    __shared__ float2 s_stat[64];
+    const int CV = C >> 3, RY = blockDim.x / CV, cpg = C / G;
+    const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+    const int n = blockIdx.y, P = gridDim.x;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(HW, row0 + rows_per_cta);
+    uint4* slab = gn_smem;
+    float2* sh = reinterpret_cast<float2*>(gn_smem + (size_t)rows_per_cta * CV);
+    const T* xn = x + (size_t)n * HW * C;
+    const T* col = xn + (size_t)tx * 8;
+    const bool active = ty < RY;                          // blockDim.x == CV * RY exactly, kept for clarity
+    unsigned int* cnt = sync + n;
+    unsigned int* gen = sync + 1024 + n;
+    unsigned int gen0 = 0;
+    if (threadIdx.x == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen0) : "l"(gen) : "memory");
+
+    // ---- phase 1: one pass over the slab: global -> registers -> (statistics, shared memory)
+    int r = row0 + ty;
+    uint4 q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (active && r + u * RY < row1) q[u] = ld_stream(col + (size_t)(r + u * RY) * C);
+    for (int g = threadIdx.x; g < G; g += blockDim.x)
+        s_piv[g] = to_f32<T>(xn[g * cpg]) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
+    __syncthreads();
+    float kk[8], S[8], SS[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = tx * 8 + j;
+        kk[j] = s_piv[c / cpg] - (add ? add[(size_t)n * C + c] : 0.f);
+        S[j] = 0.f; SS[j] = 0.f;
+    }
+    while (r < row1) {
+        const int rn = r + 8 * RY;
+        uint4 qn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (rn + u * RY < row1) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * C);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (r + u * RY < row1) {
+                slab[(size_t)(r + u * RY - row0) * CV + tx] = q[u];
+                float f[8];
+                unpack8<T>(q[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = f[j] - kk[j]; S[j] += d; SS[j] = fmaf(d, d, SS[j]); }
+            }
+        }
+        r = rn;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = qn[u];
+    }
+#if defined(TMX_GN_EXPERIMENT_STAGE) && TMX_GN_EXPERIMENT_STAGE == 1
+    if (S[0] == 123.456f) y[0] = x[0];
+    return;
+#endif
+    gn_cta_group_sums(sh, S, SS, C, CV, RY, G, cpg, tx, ty,
+                      [&](int g, float s, float ss) { part[((size_t)n * G + g) * P + blockIdx.x] = make_float2(s, ss); });
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // blockDim.x is a multiple of 32 (plan_fused)
+#if defined(TMX_GN_EXPERIMENT_STAGE) && TMX_GN_EXPERIMENT_STAGE == 2
+    return;
+#endif
+    // ---- sense-reversing barrier over the P CTAs of batch row n (arrival counter re-armed by the last arriver,
+    // generation word read at kernel entry), then EVERY CTA folds the P partials itself in the same fixed order
+    // (bit-identical statistics everywhere, and no finalise -> publish -> re-read round trips).
+    float gm[8], bt[8], ad[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                         // issued before the wait: off the critical path
+        const int c = tx * 8 + j;
+        gm[j] = gamma[c]; bt[j] = beta[c];
+        ad[j] = add ? add[(size_t)n * C + c] : 0.f;
+    }
+    __threadfence();
+    __syncthreads();
+#ifndef TMX_GN_EXPERIMENT_NOBARRIER
+    if (threadIdx.x == 0) {
+        if (atomicAdd(cnt, 1u) == (unsigned)(P - 1)) {                   // last arriver: re-arm the counter, open the barrier
+            *cnt = 0u;
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(gen), "r"(gen0 + 1u) : "memory");
+        } else {
+            unsigned int cur, polls = 0;
+            long long t0 = 0;
+            while (true) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(gen) : "memory");
+                if (cur != gen0) break;
+                if ((++polls & 1023u) == 0) {                             // bounded: a lost wake-up must trap, not hang
+                    const long long now = clock64();
+                    if (t0 == 0) t0 = now; else if (now - t0 > 4000000000LL) __trap();
+                }
+            }
+        }
+    }
+#endif
+    __syncthreads();
+    {
+        const float inv = 1.f / ((float)HW * (float)cpg);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, ss4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                     // G <= 64 and >= 16 warps... up to 4 groups per warp, loads independent
+            const int g = warp + k * nwarps;
+            if (g < G) {
+                const float2* pp = part + ((size_t)n * G + g) * P;
+                for (int i = lane; i < P; i += 32) { const float2 v = __ldcg(pp + i); s4[k] += v.x; ss4[k] += v.y; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g = warp + k * nwarps;
+            if (g < G) {
+                const float s = warp_sum(s4[k]), ss = warp_sum(ss4[k]);
+                if (lane == 0) {
+                    const float md = s * inv;
+                    const float var = fmaxf(ss * inv - md * md, 0.f);
+                    s_stat[g] = make_float2(s_piv[g] + md, rsqrtf(var + eps));
+                }
+            }
+        }
+        for (int g = warp + 4 * nwarps; g < G; g += nwarps) {              // (only for blocks of fewer than G/4 warps)
+            float s = 0.f, ss = 0.f;
+            const float2* pp = part + ((size_t)n * G + g) * P;
+            for (int i = lane; i < P; i += 32) { const float2 v = __ldcg(pp + i); s += v.x; ss += v.y; }
+            s = warp_sum(s); ss = warp_sum(ss);
+            if (lane == 0) {
+                const float md = s * inv;
+                s_stat[g] = make_float2(s_piv[g] + md, rsqrtf(fmaxf(ss * inv - md * md, 0.f) + eps));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: normalise out of shared memory
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 st = s_stat[(tx * 8 + j) / cpg];
+        a[j] = st.y * gm[j];
+        b[j] = fmaf(ad[j] - st.x, a[j], bt[j]);
+    }
+    T* ycol = y + (size_t)n * HW * C + (size_t)tx * 8;
+    for (int rr = row0 + ty; rr < row1; rr += RY) {
+        float f[8];
+        unpack8<T>(slab[(size_t)(rr - row0) * CV + tx], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = fmaf(f[j], a[j], b[j]);
+            
+#if defined(TMX_GN_EXPERIMENT_STAGE) && TMX_GN_EXPERIMENT_STAGE == 3
+            f[j] = v;
+#else
+            f[j] = act ? silu_for<T>(v) : v;
+#endif
+        }
+        st_stream(ycol + (size_t)rr * C, pack8<T>(f));
     }
 }
 
@@ -280,18 +481,25 @@ gn_apply_nchw(const T* __restrict__ x, const float* __restrict__ gamma, const fl
         float f[8];
         V8<T>::load(slab + (size_t)v * 8, f, false);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { float t = fmaf(f[j], a, b); f[j] = act ? silu(t) : t; }
+        for (int j = 0; j < 8; ++j) { float t = fmaf(f[j], a, b); f[j] = act ? silu_for<T>(t) : t; }
         V8<T>::store(yslab + (size_t)v * 8, f);
     }
 }
 
 struct GnPlan { int threads, RY, rows_per_cta, P; };
 
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+// Row lanes per CTA: as many as fit in kGnMaxThreads with CV * RY a multiple of 32 (the per-group reductions
+// use full-warp shuffles); 0 if C admits no such block (then the shape is rejected).
+static int gn_row_lanes(int CV) {
+    const int mult = 32 / gcd_int(CV, 32);
+    return (kGnMaxThreads / CV / mult) * mult;
+}
+
 static GnPlan plan_nhwc(int N, int C, int HW) {
     GnPlan p;
     const int CV = C / 8;
-    p.RY = kGnMaxThreads / CV;
-    if (p.RY > HW) p.RY = HW;
+    p.RY = gn_row_lanes(CV);
     p.threads = CV * p.RY;
     int want = (2 * sm_count() + N - 1) / N;                 // one resident wave: 2 CTAs per SM over the whole grid
     if (want < 1) want = 1;
@@ -306,8 +514,30 @@ static GnPlan plan_nhwc(int N, int C, int HW) {
     return p;
 }
 
-// workspace layout: [tickets: 1024 x u32][stat: N*G x float2][pivots (NCHW path): N*G x f32][part: N*G*kGnMaxParts x float2]
-constexpr size_t kGnTicketBytes = 1024 * sizeof(unsigned int);
+// Fused path: P = floor(#SM / N) CTAs per batch row (one CTA per SM, all co-resident), slab + scratch in shared memory.
+constexpr size_t kGnFusedSmemMax = 200 * 1024;
+struct GnFusedPlan { bool ok; int threads, rows_per_cta, P; size_t smem; };
+static int g_gn_force_two_pass = 0;      // test hook
+static GnFusedPlan plan_fused(int N, int C, int HW) {
+    GnFusedPlan p{false, 0, 0, 0, 0};
+    if (N > 1024 || N > sm_count()) return p;
+    const int CV = C / 8;
+    const int RY = gn_row_lanes(CV);
+    if (RY == 0) return p;
+    int P = sm_count() / N;
+    if (P > kGnMaxParts) P = kGnMaxParts;
+    int rows = (HW + P - 1) / P;
+    P = (HW + rows - 1) / rows;
+    p.threads = CV * RY;
+    p.rows_per_cta = rows;
+    p.P = P;
+    p.smem = (size_t)rows * C * 2 + ((size_t)RY * C + C) * sizeof(float2);
+    p.ok = p.smem <= kGnFusedSmemMax;
+    return p;
+}
+
+// workspace layout: [tickets + generations: 2048 x u32][stat: N*G x float2][pivots (NCHW path): N*G x f32][part: N*G*kGnMaxParts x float2]
+constexpr size_t kGnTicketBytes = 2048 * sizeof(unsigned int);   // [0,1024) arrival counters / tickets (left at 0), [1024,2048) fused-path barrier generations
 static size_t gn_align(size_t v) { return (v + 15) & ~(size_t)15; }
 
 template <typename T>
@@ -318,9 +548,25 @@ static int run_gn(const void* x, const float* gamma, const float* beta, const fl
     float* pivots = (float*)((char*)stat + gn_align((size_t)N * G * sizeof(float2)));
     float2* part = (float2*)((char*)pivots + gn_align((size_t)N * G * sizeof(float)));
     if (layout == TMX_NHWC) {
+        if constexpr (sizeof(T) == 2) {
+            GnFusedPlan fp = plan_fused(N, C, HW);
+            if (fp.ok && g_gn_force_two_pass != 1) {
+                const T* xx = (const T*)x; T* yy = (T*)y;
+                unsigned int* sync = tickets;
+                void* args[] = {&xx, &gamma, &beta, &add, &part, &stat, &sync, &yy, &C, &HW, &G, &fp.rows_per_cta, &eps, &act};
+                if (g_gn_force_two_pass == 2) {
+                    gn_fused_nhwc<T><<<dim3(fp.P, N), fp.threads, fp.smem, st>>>(xx, gamma, beta, add, part, stat, sync, yy, C, HW, G, fp.rows_per_cta, eps, act);
+                    return check_cuda(cudaGetLastError(), "gn_fused_nhwc launch");
+                }
+                cudaError_t e = cudaLaunchCooperativeKernel((void*)gn_fused_nhwc<T>, dim3(fp.P, N), dim3(fp.threads), args, fp.smem, st);
+                if (e == cudaSuccess) return TMX_OK;
+                if (e != cudaErrorCooperativeLaunchTooLarge) return check_cuda(e, "gn_fused_nhwc launch");
+                (void)cudaGetLastError();                                  // the device cannot co-schedule the grid: take the two-launch path
+            }
+        }
         GnPlan p = plan_nhwc(N, C, HW);
         dim3 grid(p.P, N);
-        size_t smem = (size_t)p.RY * C * sizeof(float2);
+        size_t smem = ((size_t)p.RY * C + C) * sizeof(float2);
         gn_stats_nhwc<T><<<grid, p.threads, smem, st>>>((const T*)x, add, part, stat, tickets, C, HW, G, p.rows_per_cta, eps);
         TMX_CUDA(cudaGetLastError());
         gn_apply_nhwc<T><<<grid, p.threads, 0, st>>>((const T*)x, gamma, beta, add, stat, (T*)y, C, HW, G, p.rows_per_cta, act);
@@ -339,13 +585,32 @@ static int run_gn(const void* x, const float* gamma, const float* beta, const fl
 }
 
 int groupnorm_init() {
-    // stats kernel may need up to RY*C*8 bytes = 512*8*8 = 32 KB dynamic smem: below the 48 KB default.
+    // stats kernel: (RY*C + C) float2 of dynamic smem = 32 KB + 8*C bytes: above the 48 KB default for C > 2048.
+    TMX_CUDA(cudaFuncSetAttribute(gn_stats_nhwc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    TMX_CUDA(cudaFuncSetAttribute(gn_stats_nhwc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    TMX_CUDA(cudaFuncSetAttribute(gn_stats_nhwc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    TMX_CUDA(cudaFuncSetAttribute(gn_fused_nhwc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedSmemMax));
+    TMX_CUDA(cudaFuncSetAttribute(gn_fused_nhwc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedSmemMax));
     return TMX_OK;
 }
 
 }  // namespace tmx
 
 using namespace tmx;
+
+extern "C" int tmx_groupnorm_set_variant(int v) {
+    // 0: fused single-launch path when the activation fits in shared memory (default); 1: always two launches
+    TMX_REQUIRE(v >= 0 && v <= 2, TMX_EINVAL, "groupnorm_set_variant: 0, 1 or 2");
+    g_gn_force_two_pass = v;
+    return TMX_OK;
+}
+
+extern "C" int tmx_groupnorm_launches(int N, int C, int HW, int layout, int dtype) {
+    // kernels tmx_groupnorm_fwd launches for this shape: 1 = fused cooperative kernel, 2 = stats + apply
+    if (layout == TMX_NHWC && (dtype == TMX_F16 || dtype == TMX_BF16) && g_gn_force_two_pass != 1 &&
+        N > 0 && C > 0 && HW > 0 && C % 8 == 0 && plan_fused(N, C, HW).ok) return 1;
+    return 2;
+}
 
 extern "C" size_t tmx_groupnorm_workspace_bytes(int N, int C, int HW, int G, int layout) {
     (void)C; (void)HW; (void)layout;
@@ -365,6 +630,7 @@ extern "C" int tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
     TMX_REQUIRE(aligned16(x) && aligned16(y) && aligned16(workspace), TMX_EALIGN, "groupnorm: 16-byte alignment");
     if (layout == TMX_NHWC) {
         TMX_REQUIRE(C % 8 == 0 && C / 8 <= kGnMaxThreads, TMX_ESHAPE, "groupnorm NHWC: C=%d must be a multiple of 8 and <= %d", C, 8 * kGnMaxThreads);
+        TMX_REQUIRE(gn_row_lanes(C / 8) > 0, TMX_ESHAPE, "groupnorm NHWC: no warp-aligned block for C=%d", C);
     } else if (layout == TMX_NCHW) {
         TMX_REQUIRE(HW % 8 == 0, TMX_ESHAPE, "groupnorm NCHW: HW=%d must be a multiple of 8", HW);
     } else {

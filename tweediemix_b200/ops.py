@@ -217,7 +217,7 @@ def group_norm(x, gamma, beta, groups: int, eps: float, *, silu=False, add=None,
         assert add.dtype == torch.float32 and add.is_contiguous() and add.shape == (N, Cc)
     lib = _lib.load()
     ws = _workspace(d, lib.tmx_groupnorm_workspace_bytes(N, Cc, H * W, groups, layout))
-    with _Launch("groupnorm", 2, f"C{Cc}_HW{H * W}", 2.0 * x.numel() * x.element_size()):
+    with _Launch("groupnorm", lib.tmx_groupnorm_launches(N, Cc, H * W, layout, _dt(x)), f"C{Cc}_HW{H * W}", 2.0 * x.numel() * x.element_size()):
         rc = lib.tmx_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(add), _p(out), _p(ws), N, Cc, H * W, groups,
                                    float(eps), _lib.ACT_SILU if silu else _lib.ACT_NONE, layout, _dt(x), _stream())
     _lib.check(rc, "tmx_groupnorm_fwd")
