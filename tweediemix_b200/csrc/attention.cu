@@ -197,6 +197,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
         :: "r"(taddr), TMX_I8(r, 0), TMX_I8(r, 8), TMX_I8(r, 16), TMX_I8(r, 24) : "memory");
 }
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, "
+        "%33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, "
+        "%49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};"
+        :: "r"(taddr), TMX_I8(r, 0), TMX_I8(r, 8), TMX_I8(r, 16), TMX_I8(r, 24), TMX_I8(r, 32), TMX_I8(r, 40), TMX_I8(r, 48), TMX_I8(r, 56)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -616,37 +626,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const int chunks = last ? last_chunks : NCH;
                 const uint64_t nm2 = pk2(-m_new, -m_new);
                 uint64_t sum_a = pk2(0.f, 0.f), sum_b = pk2(0.f, 0.f);
-#pragma unroll
-                for (int q = 0; q < NCH; ++q) {
-                    if (q < chunks) {
-                        uint32_t p[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const uint64_t x2 = ffma2(pk2(__uint_as_float(s[q * 32 + 2 * c]), __uint_as_float(s[q * 32 + 2 * c + 1])), sc2, nm2);
-                            float e0, e1;
-                            if (kPolyEvery > 0 && (c % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
-                                ex2_poly2(x2, e0, e1);
-                            } else {
-                                float x0, x1;
-                                upk2(x2, x0, x1);
+                // exponentials of one pair of columns (MUFU, or the FMA-pipe polynomial for one pair in kPolyEvery)
+                auto exp_pair = [&](int col, int c, uint32_t& packed) {
+                    const uint64_t x2 = ffma2(pk2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sc2, nm2);
+                    float e0, e1;
+                    if (kPolyEvery > 0 && (c % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+                        ex2_poly2(x2, e0, e1);
+                    } else {
+                        float x0, x1;
+                        upk2(x2, x0, x1);
 #ifdef TMX_ATTN_EXPERIMENT_NOEXP
-                                e0 = x0; e1 = x1;
+                        e0 = x0; e1 = x1;
 #else
-                                e0 = ex2(x0);
-                                e1 = ex2(x1);
+                        e0 = ex2(x0);
+                        e1 = ex2(x1);
 #endif
-                            }
-                            if (c & 1) sum_b = fadd2(sum_b, pk2(e0, e1)); else sum_a = fadd2(sum_a, pk2(e0, e1));
-                            p[c] = pack2<BF16>(e0, e1);
+                    }
+                    if (c & 1) sum_b = fadd2(sum_b, pk2(e0, e1)); else sum_a = fadd2(sum_a, pk2(e0, e1));
+                    packed = pack2<BF16>(e0, e1);
+                };
+                if (!pv_waited && j > 0) {                                 // P(n-1) must have been consumed before it is overwritten;
+                    mbar_wait(bar_pv_done, (n - 1u) & 1u);                 // P V(n-1) was issued a whole load + max phase ago: normally ready
+                    tc_fence_after();
+                }
+                TMX_TRACE(23);
+                if (chunks == NCH) {
+                    // full tile: ONE straight-line block over all columns (no per-chunk branches or stores in between, so
+                    // the tail of one chunk's MUFU / convert chain overlaps the head of the next), one wide P store
+                    uint32_t p[COLS / 2];
+#pragma unroll
+                    for (int c = 0; c < COLS / 2; ++c) exp_pair(2 * c, c, p[c]);
+                    TMX_TRACE(22);
+                    if constexpr (HV == 1) tmem_st64(t_row + 192, p);
+                    else tmem_st32(t_row + 192 + half * (COLS / 2), p);
+                } else {
+                    // partial last K/V tile (cross-attention, Nk = 77): only the chunks that hold valid columns
+#pragma unroll
+                    for (int q = 0; q < NCH; ++q) {
+                        if (q < chunks) {
+                            uint32_t p[16];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) exp_pair(q * 32 + 2 * c, c, p[c]);
+                            tmem_st16(t_row + 192 + half * (COLS / 2) + q * 16, p);
                         }
-                        if (q == 0) TMX_TRACE(22);
-                        if (!pv_waited && j > 0) {                         // P(n-1) must have been consumed before it is overwritten
-                            mbar_wait(bar_pv_done, (n - 1u) & 1u);
-                            tc_fence_after();
-                            pv_waited = true;
-                        }
-                        if (q == 0) TMX_TRACE(23);
-                        tmem_st16(t_row + 192 + half * (COLS / 2) + q * 16, p);
                     }
                 }
                 {
