@@ -42,7 +42,7 @@ constexpr int kBN = 128;             // kv rows per tile     (UMMA N of QK^T, K 
 constexpr int kTileBytes = kBM * kD * 2;         // 16 KiB, one 128x64 16-bit tile
 constexpr float kRescaleThreshold = 8.0f;        // log2 domain
 #ifndef TMX_ATTN_POLY_EVERY
-#define TMX_ATTN_POLY_EVERY 4
+#define TMX_ATTN_POLY_EVERY 3
 #endif
 constexpr int kPolyEvery = TMX_ATTN_POLY_EVERY;  // one PAIR of exponentials in every kPolyEvery pairs goes to the FMA pipe (0 = all MUFU)
 
