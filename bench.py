@@ -302,7 +302,8 @@ def run_ours(args):
             ach = work / (ms * 1e-3) / 1e12
             roof = {"kernel": "attn_fwd_kernel (tcgen05 self-attention, all launches of one fused step)", "bound": "tensor",
                     "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})", "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                    **_ncu_attention_traffic({tag: d["launches"] for tag, d in self_attn}),
                     "launches": n, "avg_launch_ms": ms / n, "flops_per_launch": work / n,
                     "by_shape": {tag: {"launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
                                        "tflops": d["work"] / (d["ms"] * 1e-3) / 1e12} for tag, d in fam["attention"]}}
@@ -371,6 +372,30 @@ def run_ours(args):
 
 
 _JSON_FD = None
+
+
+def _ncu_attention_traffic(launches_by_tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the attention kernel, from the committed
+    `ncu --set full` summaries under profiles/ (one capture per self-attention shape), weighted by this step's launch mix."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.abspath(__file__))
+    per_shape, used = {}, []
+    for tag in launches_by_tag:
+        m = re.match(r"Nq(\d+)_Nk(\d+)", tag)
+        files = sorted(glob.glob(os.path.join(root, "profiles", f"r*_ncu_attn_n{m.group(1)}_final.txt"))) if m and m.group(1) == m.group(2) else []
+        if not files:
+            return {"traffic": None}
+        tot = 0.0
+        for line in open(files[-1]):
+            mm = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if mm:
+                tot += float(mm.group(2)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[mm.group(3)]
+        per_shape[tag] = tot
+        used.append(os.path.basename(files[-1]))
+    n = sum(launches_by_tag.values())
+    return {"traffic": sum(per_shape[t] * c for t, c in launches_by_tag.items()) / n,
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, launch-weighted over " + ", ".join(used)}
 
 
 def _protect_stdout():

@@ -417,6 +417,14 @@ def main(argv=None, lora: bool = False):
         components = make_components(concept_num=k, variant=variant, seed=opt.seed, device=opt.device,
                                      dtype=torch.bfloat16 if opt.dtype == 'bf16' else torch.float16,
                                      latent_hw=(opt.resolution_h // 8, opt.resolution_w // 8))
+        if opt.personal_checkpoint:
+            # real concept checkpoints (delta-*.bin, '+'-separated) on the seeded base U-Net: the reader of
+            # fusion_sampling.py:157-158,203-210 / fusion_sampling_lora.py:203-210
+            from .checkpoints import concept_from_checkpoint
+            paths = opt.personal_checkpoint.split('+')
+            if len(paths) != k:
+                raise ValueError(f"--personal_checkpoint names {len(paths)} files for {k} concepts")
+            components.concept_unets = [concept_from_checkpoint(components.unet, pth, variant) for pth in paths]
     model = Tweediemix(opt, components, variant=variant)
     if opt.masks_dir:
         model.set_masks(load_region_masks(opt.masks_dir, opt.seg_concepts, opt.resolution_h // 8, opt.resolution_w // 8))
