@@ -144,7 +144,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "1024px images/sec @50 DDIM steps, K concepts", "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / val,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1, 1), "gpu_launches": 0,
+            "config": workload_config(args, min(max(args.gpus, 1), K_CONCEPTS + 1), max(max(args.gpus, 1) // min(max(args.gpus, 1), K_CONCEPTS + 1), 1)),
+            "gpu_launches": 0,
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": ref.threads, "kind": "port", "sample": ref.sample_description(),
                              "seconds_per_sample_forward": sec},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -94,3 +94,34 @@ def test_attention_errors():
     z32 = torch.zeros(1, 8, 64).cuda()
     with pytest.raises(RuntimeError, match="dtype"):
         o.attention(z32, z32, z32, 1)
+
+
+FULL = [(4, 10, 4096, 4096), (4, 20, 1024, 1024), (4, 10, 4096, 77), (4, 20, 1024, 77)]
+
+
+@pytest.mark.parametrize("shape", FULL)
+def test_attention_full_size_properties(shape):
+    """Size-independent properties at the SDXL 1024x1024 shapes (no N x N reference needed):
+    (1) V == 1 -> every output is 1: the row sum accumulated by the softmax warps and the P the tensor core consumes
+        are the same numbers (a dropped / double-counted tile or column shows up immediately);
+    (2) softmax is invariant to a per-row logit shift: adding a constant vector c to every KEY changes each logit row by
+        q.c (constant along the softmax axis) and must not change the output beyond rounding;
+    (3) permuting the K/V rows together leaves the output unchanged up to summation order."""
+    o = ops()
+    B, H, Nq, Nk = shape
+    g = torch.Generator(device="cuda").manual_seed(Nq + Nk)
+    q = torch.randn(B, Nq, H * 64, generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, Nk, H * 64, generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, Nk, H * 64, generator=g, device="cuda").to(torch.bfloat16)
+    ones = o.attention(q, k, torch.ones_like(v), H)
+    assert (ones.float() - 1).abs().max().item() <= 2 ** -7
+    base = o.attention(q, k, v, H)
+    perm = torch.randperm(Nk, generator=torch.Generator().manual_seed(1)).cuda()
+    shuffled = o.attention(q, k[:, perm].contiguous(), v[:, perm].contiguous(), H)
+    assert (base.float() - shuffled.float()).abs().max().item() <= 3e-2
+    kf = k.float().reshape(B, Nk, H, 64)
+    c = 0.25 * torch.randn(1, 1, H, 64, generator=g, device="cuda")
+    shifted = o.attention(q, (kf + c).reshape(B, Nk, H * 64).to(torch.bfloat16), v, H)
+    # (k + c) is re-rounded to bf16, so the shift is only approximately constant per row: |dlogit| <= 2^-8 |k+c| |q| / 8
+    assert (base.float() - shifted.float()).abs().max().item() <= 6e-2
+    assert (base.float() - shifted.float()).abs().mean().item() <= 4e-3

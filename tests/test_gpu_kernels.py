@@ -292,3 +292,30 @@ def test_residual_add_layernorm(dtype, shape):
     assert torch.equal(h.cpu(), h_want)
     torch.testing.assert_close(n.cpu().float(), n_want.to(dtype).float(), rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
     assert torch.equal(n.cpu(), o.layer_norm(h_want.cuda(), gamma.cuda(), beta.cuda(), 1e-5).cpu())
+
+
+def test_blend_full_size_properties_2048_images():
+    """BASELINE-size properties of k7 that need no oracle run (2048 stacked 128x128 images, 2.1 GB):
+    (1) per-image independence — every image of the stack equals the single-image launch on its slice;
+    (2) partition property — when all concept rows carry the SAME eps, a perfect partition of masks blends to the
+        plain single-prompt CFG step (fusion_sampling.py:376-386 collapses to :425-430);
+    (3) t == 1 returns x0 (:471-472)."""
+    o = ops()
+    K, h, w, imgs = 3, 128, 128, 2048
+    masks = synth.fixture_masks(h, w).cuda()
+    assert torch.equal(masks.sum(0), torch.ones_like(masks[0]))          # the example masks are a perfect partition
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(imgs, 4, h, w, generator=g, device="cuda")
+    eps = torch.randn(imgs, K + 1, 4, h, w, generator=g, device="cuda").to(torch.bfloat16)
+    got = o.tweedie_blend_ddim(x, eps, masks, 0.0438, 0.0518, 0.8)
+    for i in (0, 777, imgs - 1):
+        one = o.tweedie_blend_ddim(x[i:i + 1].contiguous(), eps[i:i + 1].contiguous(), masks, 0.0438, 0.0518, 0.8)
+        assert torch.equal(got[i:i + 1], one)
+    same = eps.clone()
+    same[:, 2:] = same[:, 1:2]
+    blended = o.tweedie_blend_ddim(x, same, masks, 0.0438, 0.0518, 0.8)
+    plain = o.tweedie_blend_ddim(x, same[:, :2].contiguous(), None, 0.0438, 0.0518, 0.8)
+    torch.testing.assert_close(blended, plain, rtol=2e-5, atol=2e-4)
+    x0 = torch.empty_like(x)
+    last = o.tweedie_blend_ddim(x, eps, masks, 0.99915, 0.99915, 0.8, is_last=True, x0_out=x0)
+    assert torch.equal(last, x0)
