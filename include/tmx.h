@@ -192,17 +192,23 @@ TMX_API int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o,
 TMX_API int tmx_attn_set_variant(int nq);
 
 /* ---------------------------------------------------------------------------------------------
- * k3 — per-row routed projection (grouped GEMM over batch rows, one weight matrix per row):
- *   y[b] = x[b] @ W[b]^T (+ (x[b] @ down[b]^T) @ up[b]^T)          b = 0..B-1
- * Replaces the per-row nn.Linear + torch.cat of utils_custom.py:64-82 (concept K/V weights) and
- * the rank-r LoRA deltas of utils_lora.py:65-79,113-119 / model_lora.py:41-48.
- * x : dtype [B, M, Kin];  w : HOST array of B device pointers to dtype [Nout, Kin];
- * lora_down / lora_up : HOST arrays of B device pointers ([r, Kin] / [Nout, r]) or NULL entries
- * (NULL array = no LoRA anywhere);  y : dtype [B, M, Nout].
+ * k3 — per-row routed projection: one weight matrix and / or one set of rank-r LoRA factors per batch row
+ *   w != NULL        :  y[b]  = x[b] @ W[b]^T                                   (grouped tcgen05 GEMM)
+ *   lora_* != NULL   :  y[b] += per segment s: (x[b] @ down[b][s]^T) @ up[b][cols of s]^T   (rank-r delta)
+ * With w == NULL the call only ADDS the LoRA deltas to a y that already holds the shared-weight projection.
+ * Replaces the per-row nn.Linear + torch.cat of utils_custom.py:64-82 (concept K/V weights) and the rank-r LoRA
+ * deltas of utils_lora.py:65-79,113-119 / model_lora.py:28-48.
+ * x : dtype [B, M, Kin] contiguous;  y : dtype [B, M, Nout] contiguous;  B <= 16, Kin % 64 == 0, Nout % 8 == 0
+ * w : HOST array of B device pointers to dtype [Nout, Kin] (all non-NULL), or NULL
+ * lora_down / lora_up : HOST arrays of B device pointers to dtype [nseg*rank, Kin] / [Nout, rank]; a NULL ENTRY
+ *   (in both arrays) leaves that batch row untouched (row 0, the unconditional row, is never routed); NULL arrays =
+ *   no LoRA.  Output column n belongs to segment n / (Nout / nseg) — a packed q|k|v projection is nseg = 3 — and
+ *   uses rows [s*rank, (s+1)*rank) of down;  nseg*rank in {4, 8, 12, 16}.
+ * fp32 accumulation, one rounding per store.  Algorithmic FLOPs: 2*B*M*Kin*Nout (+ 2*B*M*rank*(nseg*Kin + Nout)).
  */
 TMX_API int tmx_routed_linear_fwd(const void* x, const void* const* w, const void* const* lora_down,
                           const void* const* lora_up, void* y, int B, int M, int Kin, int Nout,
-                          int rank, int dtype, void* stream);
+                          int rank, int nseg, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

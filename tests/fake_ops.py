@@ -72,6 +72,28 @@ def attention(q, k, v, heads, scale=None, out=None):
     return (p @ vh).permute(0, 2, 1, 3).reshape(B, Nq, HD).to(q.dtype)
 
 
+def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg=1, out=None):
+    B, M, Kin = x.shape
+    if weights is not None:
+        y = torch.stack([x[b].float() @ weights[b].float().t() for b in range(B)]).to(x.dtype)
+        if out is not None:
+            out.copy_(y)
+        else:
+            out = y
+    if lora_down is not None:
+        Nout = out.shape[-1]
+        seg = Nout // nseg
+        for b in range(B):
+            if lora_down[b] is None:
+                continue
+            r = lora_down[b].shape[0] // nseg
+            t = x[b].float() @ lora_down[b].float().t()                       # [M, nseg*r]
+            for s_ in range(nseg):
+                up = lora_up[b][s_ * seg:(s_ + 1) * seg].float()              # [seg, r]
+                out[b, :, s_ * seg:(s_ + 1) * seg] += (t[:, s_ * r:(s_ + 1) * r] @ up.t()).to(out.dtype)
+    return out
+
+
 def _mw(masks, weights, K, like):
     m = masks if masks is not None else torch.ones(K, 1, 1, 1, device=like.device)
     if weights is not None:
@@ -118,5 +140,5 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
 
 def install(monkeypatch):
     from tweediemix_b200 import ops
-    for name in ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish"):
+    for name in ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -319,3 +319,75 @@ def test_blend_full_size_properties_2048_images():
     x0 = torch.empty_like(x)
     last = o.tweedie_blend_ddim(x, eps, masks, 0.99915, 0.99915, 0.8, is_last=True, x0_out=x0)
     assert torch.equal(last, x0)
+
+
+# ------------------------------------------------------------------------------------------ k3
+def _routed_ref(x, weights, downs, ups, nseg, base=None):
+    """fp32 restatement of utils_custom.py:64-82 (per-row weights) / utils_lora.py:65-79 (rank-r deltas per row)."""
+    B = x.shape[0]
+    y = torch.stack([x[b].float() @ weights[b].float().t() for b in range(B)]) if weights is not None else base.float().clone()
+    if downs is not None:
+        seg = y.shape[-1] // nseg
+        for b in range(B):
+            if downs[b] is None:
+                continue
+            r = downs[b].shape[0] // nseg
+            t = x[b].float() @ downs[b].float().t()
+            for s in range(nseg):
+                y[b, :, s * seg:(s + 1) * seg] += t[:, s * r:(s + 1) * r] @ ups[b][s * seg:(s + 1) * seg].float().t()
+    return y
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(4, 77, 2048, 2560), (4, 77, 2048, 1280), (2, 5, 64, 8), (3, 130, 128, 136), (1, 256, 640, 640),
+                                   (9, 77, 2048, 2560)])   # B, M, Kin, Nout; the first two are the SDXL cross-attention K/V sites
+def test_routed_linear_grouped_gemm(dtype, shape):
+    """k3 grouped tcgen05 GEMM: one weight matrix per batch row, vs fp32 matmul of the same 16-bit inputs.
+    Tolerance: fp32 accumulation, one rounding of the output dtype."""
+    o = ops()
+    B, M, Kin, Nout = shape
+    g = torch.Generator().manual_seed(M + Nout)
+    x = torch.randn(B, M, Kin, generator=g).to(dtype).cuda()
+    ws = [(torch.randn(Nout, Kin, generator=g) / Kin ** 0.5).to(dtype).cuda() for _ in range(B)]
+    got = o.routed_linear(x, ws)
+    want = _routed_ref(x, ws, None, None, 1)
+    assert got.shape == (B, M, Nout) and torch.isfinite(got.float()).all()
+    torch.testing.assert_close(got.float(), want.to(dtype).float(), rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(4, 1024, 1280, 3840, 3), (4, 4096, 640, 1920, 3), (4, 77, 2048, 2560, 2), (4, 1024, 1280, 1280, 1),
+                                   (2, 37, 64, 64, 1), (3, 5, 128, 48, 3)])   # B, M, Kin, Nout, nseg — rank 4 (model_lora.py:28-48)
+def test_routed_linear_lora_delta(dtype, shape):
+    """k3 rank-r delta kernel: row 0 (unconditional) untouched, rows 1.. get segment-wise (x down^T) up^T added in place."""
+    o = ops()
+    B, M, Kin, Nout, nseg = shape
+    r = 4
+    g = torch.Generator().manual_seed(M + Nout + nseg)
+    x = torch.randn(B, M, Kin, generator=g).to(dtype).cuda()
+    base = torch.randn(B, M, Nout, generator=g).to(dtype).cuda()
+    downs = [None] + [(torch.randn(nseg * r, Kin, generator=g) / r).to(dtype).cuda() for _ in range(B - 1)]
+    ups = [None] + [(torch.randn(Nout, r, generator=g) * 0.05).to(dtype).cuda() for _ in range(B - 1)]
+    y = base.clone()
+    got = o.routed_linear(x, None, downs, ups, nseg=nseg, out=y)
+    assert got.data_ptr() == y.data_ptr() and torch.equal(y[0], base[0])
+    want = _routed_ref(x, None, downs, ups, nseg, base=base)
+    torch.testing.assert_close(y.float(), want.to(dtype).float(), rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=4e-3)
+
+
+def test_routed_linear_weights_plus_lora_and_errors():
+    o = ops()
+    g = torch.Generator().manual_seed(2)
+    B, M, Kin, Nout, r = 3, 77, 128, 256, 4
+    x = torch.randn(B, M, Kin, generator=g).to(torch.bfloat16).cuda()
+    ws = [(torch.randn(Nout, Kin, generator=g) / Kin ** 0.5).to(torch.bfloat16).cuda() for _ in range(B)]
+    downs = [None] + [(torch.randn(2 * r, Kin, generator=g) / r).to(torch.bfloat16).cuda() for _ in range(B - 1)]
+    ups = [None] + [(torch.randn(Nout, r, generator=g) * 0.05).to(torch.bfloat16).cuda() for _ in range(B - 1)]
+    got = o.routed_linear(x, ws, downs, ups, nseg=2)
+    # the GEMM result is rounded to bf16 before the delta is added (two kernels): allow two output roundings
+    want = _routed_ref(x, ws, downs, ups, 2)
+    torch.testing.assert_close(got.float(), want, rtol=2 ** -6, atol=6e-3)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        o.routed_linear(torch.zeros(1, 4, 48, dtype=torch.bfloat16).cuda(), [torch.zeros(8, 48, dtype=torch.bfloat16).cuda()])
+    with pytest.raises(RuntimeError, match="B=17"):
+        o.routed_linear(torch.zeros(17, 4, 64, dtype=torch.bfloat16).cuda(), [torch.zeros(8, 64, dtype=torch.bfloat16).cuda()] * 17)

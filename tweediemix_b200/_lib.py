@@ -39,7 +39,7 @@ SIGNATURES = {
     "tmx_geglu_fwd": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
     "tmx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _f, _i, _vp]),
     "tmx_attn_set_variant": (_i, [_i]),
-    "tmx_routed_linear_fwd": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "tmx_routed_linear_fwd": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -15,6 +15,7 @@
 // Replaces [D] diffusers ResnetBlock2D norm1/norm2 + SiLU (mirrored in the reference at
 // video_gen/utils_attn.py:391-431), conv_norm_out + SiLU, and Transformer2DModel.norm (no act).
 #include "tmx_common.cuh"
+#include <cstdlib>
 
 namespace tmx {
 
@@ -585,6 +586,8 @@ static int run_gn(const void* x, const float* gamma, const float* beta, const fl
 }
 
 int groupnorm_init() {
+    // TMX_GN_TWO_PASS=1 forces the two-launch path (ncu's kernel replay cannot re-run the fused kernel's inter-CTA barrier)
+    if (const char* e = getenv("TMX_GN_TWO_PASS")) g_gn_force_two_pass = (e[0] == '1') ? 1 : g_gn_force_two_pass;
     // stats kernel: (RY*C + C) float2 of dynamic smem = 32 KB + 8*C bytes: above the 48 KB default for C > 2048.
     TMX_CUDA(cudaFuncSetAttribute(gn_stats_nhwc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     TMX_CUDA(cudaFuncSetAttribute(gn_stats_nhwc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));

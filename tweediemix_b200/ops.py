@@ -308,6 +308,47 @@ def geglu(x, out=None):
     return out
 
 
+# ------------------------------------------------------------------------------------------ k3
+
+def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg: int = 1, out=None):
+    """Per-row routed projection (``utils_custom.py:64-82``, ``utils_lora.py:65-79,113-119``).
+
+    ``x`` [B, M, Kin].  ``weights``: list of B tensors [Nout, Kin] -> ``out[b] = x[b] @ weights[b].T`` (grouped tcgen05
+    GEMM); ``None`` -> ``out`` must already hold the shared-weight projection.  ``lora_down`` / ``lora_up``: lists of B
+    entries, each a tensor ([nseg*r, Kin] / [Nout, r]) or ``None`` (row not routed) -> the rank-r deltas are ADDED to
+    ``out``; output column n uses segment ``n // (Nout // nseg)`` (packed q|k|v: nseg = 3)."""
+    _dev(x, out)
+    assert x.dim() == 3 and x.is_contiguous(), "x must be a contiguous [B, M, Kin] tensor"
+    B, M, Kin = x.shape
+    if weights is not None:
+        assert len(weights) == B
+        Nout = weights[0].shape[0]
+        for w in weights:
+            assert w.dtype == x.dtype and w.is_cuda and w.is_contiguous() and tuple(w.shape) == (Nout, Kin)
+        if out is None:
+            out = torch.empty((B, M, Nout), dtype=x.dtype, device=x.device)
+    else:
+        assert out is not None and lora_down is not None, "without weights the call accumulates LoRA deltas into `out`"
+        Nout = out.shape[-1]
+    assert out.is_contiguous() and tuple(out.shape) == (B, M, Nout) and out.dtype == x.dtype
+    rank = 0
+    if lora_down is not None:
+        assert lora_up is not None and len(lora_down) == B and len(lora_up) == B
+        for d, u in zip(lora_down, lora_up):
+            assert (d is None) == (u is None)
+            if d is not None:
+                rank = d.shape[0] // nseg
+                assert d.dtype == x.dtype and u.dtype == x.dtype and d.is_contiguous() and u.is_contiguous()
+                assert tuple(d.shape) == (nseg * rank, Kin) and tuple(u.shape) == (Nout, rank), (d.shape, u.shape, nseg, Nout)
+    arr = lambda ts: (C.c_void_p * B)(*[None if t is None else t.data_ptr() for t in ts]) if ts is not None else None
+    wp, dp, up = arr(weights), arr(lora_down), arr(lora_up)
+    launches = (1 if weights is not None else 0) + (1 if rank else 0)
+    with _Launch("routed_linear", launches, f"M{M}_K{Kin}_N{Nout}", 2.0 * B * M * Kin * Nout if weights is not None else 0.0):
+        rc = _lib.load().tmx_routed_linear_fwd(_p(x), wp, dp, up, _p(out), B, M, Kin, Nout, int(rank), int(nseg), _dt(x), _stream())
+    _lib.check(rc, "tmx_routed_linear_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ k1/k2
 
 def attention(q, k, v, heads: int, scale: float | None = None, out=None):

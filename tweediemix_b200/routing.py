@@ -13,6 +13,8 @@ from typing import List, Optional
 import torch
 import torch.nn.functional as F
 
+from . import ops
+
 _next_tag = [0]
 
 
@@ -41,10 +43,8 @@ class CustomRouting:
         if ehs.shape[0] != len(self.kv_weights):
             raise RuntimeError(f"routing built for {len(self.kv_weights)} rows, got batch {ehs.shape[0]}")
         base = attn.packed_kv()
-        out = torch.empty(ehs.shape[0], ehs.shape[1], base.shape[0], dtype=ehs.dtype, device=ehs.device)
-        for r, w in enumerate(self.kv_weights):
-            torch.matmul(ehs[r], (base if w is None else w).t(), out=out[r])
-        return out
+        # k3: ONE grouped tcgen05 GEMM over the batch rows, each with its own [2*inner, cross_dim] weight
+        return ops.routed_linear(ehs.contiguous(), [base if w is None else w for w in self.kv_weights])
 
 
 class LoRARows:
@@ -53,15 +53,16 @@ class LoRARows:
     def __init__(self, q, k, v, out):
         # each argument: (down [r, in], up [out, r])
         (dq, uq), (dk, uk), (dv, uv), (do, uo) = q, k, v, out
-        self.q_down, self.q_up_t = dq.contiguous(), uq.t().contiguous()
-        self.out_down, self.out_up_t = do.contiguous(), uo.t().contiguous()
+        # k3 layout: down [nseg*r, in] (segments stacked), up [Nout, r] (segments stacked along the output columns)
+        self.q_down, self.q_up = dq.contiguous(), uq.contiguous()
+        self.out_down, self.out_up = do.contiguous(), uo.contiguous()
         self.kv_down = torch.cat([dk, dv]).contiguous()                       # [2r, in_kv]
-        self.kv_up_t = torch.block_diag(uk, uv).t().contiguous()              # [2r, 2*inner]
+        self.kv_up = torch.cat([uk, uv]).contiguous()                         # [2*inner, r]
         if dq.shape[1] == dk.shape[1]:                                        # self-attention: q, k, v share the input
             self.qkv_down = torch.cat([dq, dk, dv]).contiguous()              # [3r, d]
-            self.qkv_up_t = torch.block_diag(uq, uk, uv).t().contiguous()     # [3r, 3*inner]
+            self.qkv_up = torch.cat([uq, uk, uv]).contiguous()                # [3*inner, r]
         else:
-            self.qkv_down = self.qkv_up_t = None
+            self.qkv_down = self.qkv_up = None
 
 
 class LoRARouting:
@@ -72,6 +73,7 @@ class LoRARouting:
         self.rows = rows
         self.cache_tag = _tag()
         self._subsets = {}
+        self._lists = {}
 
     def subset(self, row_ids):
         key = tuple(row_ids)
@@ -83,29 +85,36 @@ class LoRARouting:
         if batch != len(self.rows):
             raise RuntimeError(f"routing built for {len(self.rows)} rows, got batch {batch}")
 
-    def add_qkv_self(self, attn, x, qkv):
+    def _factors(self, which: str):
+        """(downs, ups) per batch row for projection ``which`` ('qkv', 'q', 'kv', 'out'); ``None`` entries = not routed."""
+        got = self._lists.get(which)
+        if got is None:
+            got = ([None if lr is None else getattr(lr, which + "_down") for lr in self.rows],
+                   [None if lr is None else getattr(lr, which + "_up") for lr in self.rows])
+            self._lists[which] = got
+        return got
+
+    def _add(self, which: str, nseg: int, x, y):
+        """y[r] += segment-wise (x[r] @ down_r^T) @ up_r^T for every routed row r: ONE k3 launch for the whole batch."""
         self._check(x.shape[0])
-        for r, lr in enumerate(self.rows):
-            if lr is not None:
-                qkv[r].addmm_(F.linear(x[r], lr.qkv_down), lr.qkv_up_t)
+        downs, ups = self._factors(which)
+        if all(d is None for d in downs):
+            return y
+        if not (x.is_contiguous() and y.is_contiguous()):
+            raise RuntimeError("LoRA routing needs contiguous activations")
+        return ops.routed_linear(x, None, downs, ups, nseg=nseg, out=y)
+
+    def add_qkv_self(self, attn, x, qkv):
+        self._add("qkv", 3, x, qkv)
 
     def add_q(self, attn, x, q):
-        self._check(x.shape[0])
-        for r, lr in enumerate(self.rows):
-            if lr is not None:
-                q[r].addmm_(F.linear(x[r], lr.q_down), lr.q_up_t)
+        self._add("q", 1, x, q)
 
     def kv_rows(self, attn, ehs):
-        self._check(ehs.shape[0])
+        ehs = ehs.contiguous()
         kv = F.linear(ehs, attn.packed_kv())
-        for r, lr in enumerate(self.rows):
-            if lr is not None:
-                kv[r].addmm_(F.linear(ehs[r], lr.kv_down), lr.kv_up_t)
-        return kv
+        return self._add("kv", 2, ehs, kv)
 
     def add_out(self, attn, a, o):
         """delta from the PRE-``to_out[0]`` tensor, added after its bias (utils_lora.py:113-119)."""
-        self._check(a.shape[0])
-        for r, lr in enumerate(self.rows):
-            if lr is not None:
-                o[r].addmm_(F.linear(a[r], lr.out_down), lr.out_up_t)
+        self._add("out", 1, a, o)
