@@ -14,7 +14,7 @@
 // and columns beyond Nout are zero-filled by TMA on the way in and masked on the way out.  The text-only cross-attention
 // K/V of the custom variant (M = 77) is the intended shape: one launch instead of K+1 cuBLAS calls, W[b] streamed once.
 //
-// LoRA delta: one warp per token row, 4 rows per warp, 8 warps per CTA; down[b] / up[b] converted to fp32 in shared
+// LoRA delta: one warp per token row, 3 rows per warp, 8 warps per CTA; down[b] / up[b] converted to fp32 in shared
 // memory once per CTA; t = x_row . down^T by lane-strided 128-bit loads + warp reduction, then a read-modify-write of
 // the y row.  Output column n belongs to segment s = n / (Nout / nseg) and uses t[s*r .. s*r + r): a packed q|k|v
 // projection is ONE launch with nseg = 3 and no block-diagonal zero padding.
@@ -220,11 +220,11 @@ routed_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
 // ------------------------------------------------------------------------------------------- LoRA delta
 struct LoraPtrs { const void* down[kMaxRows]; const void* up[kMaxRows]; };
-constexpr int kLoraWarps = 8, kLoraRowsPerWarp = 4;
+constexpr int kLoraWarps = 8, kLoraRowsPerWarp = 3;   // 24 rows per CTA: the 3 x 1024 routed rows of a 32x32 site fill 128 CTAs = one wave
 constexpr size_t kLoraSmemMax = 200 * 1024;
 
 // y[b, m, n] += sum_j t[seg(n) * r + j] * up[b][n, j],   t[q] = sum_k x[b, m, k] * down[b][q, k]
-// SR = nseg * r (4, 8, 12 or 16).  smem: down as fp32 [SR][Kin], up as fp32 [Nout][r].
+// SR = nseg * r (4, 8, 12 or 16).  smem: down as fp32 [SR][Kin], up as fp32 TRANSPOSED [r][Nout] (conflict-free column reads).
 template <typename T, int SR>
 __global__ void __launch_bounds__(kLoraWarps * 32, 1)
 lora_delta_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constant__ LoraPtrs ptrs,
@@ -235,19 +235,23 @@ lora_delta_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_const
     const T* up = reinterpret_cast<const T*>(ptrs.up[b]);
     if (down == nullptr) return;                               // this batch row is not routed (row 0: the unconditional row)
     float* s_down = lora_smem;                                 // [SR][Kin]
-    float* s_up = lora_smem + (size_t)SR * Kin;                // [Nout][r]
+    float* s_up = lora_smem + (size_t)SR * Kin;                // [r][Nout]  (transposed: lanes read consecutive columns)
     __shared__ float s_t[kLoraWarps][16];                      // per-warp t, so the segment lookup is a (broadcast) smem read
     for (int i = threadIdx.x; i < SR * Kin / 8; i += blockDim.x) {
         float f[8];
         unpack8<T>(ld_keep(down + (size_t)i * 8), f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s_down[(size_t)i * 8 + e] = f[e];
+        *reinterpret_cast<float4*>(s_down + (size_t)i * 8) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(s_down + (size_t)i * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
     }
     for (int i = threadIdx.x; i < Nout * r / 8; i += blockDim.x) {
         float f[8];
         unpack8<T>(ld_keep(up + (size_t)i * 8), f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s_up[(size_t)i * 8 + e] = f[e];
+        for (int e = 0; e < 8; ++e) {
+            const int idx = i * 8 + e;                         // element (n, j) of up[Nout][r]
+            const int n = idx / r, j = idx - n * r;
+            s_up[(size_t)j * Nout + n] = f[e];
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -283,12 +287,12 @@ lora_delta_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_const
             const float* ts = &s_t[warp][((v * 8) / seg_cols) * r];  // 8 consecutive columns never straddle a segment (seg_cols % 8 == 0)
             float f[8];
             unpack8<T>(ld_keep(yr + (size_t)v * 8), f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float* u = s_up + (size_t)(v * 8 + e) * r;
-                float acc = f[e];
-                for (int j = 0; j < r; ++j) acc = fmaf(ts[j], u[j], acc);
-                f[e] = acc;
+            for (int j = 0; j < r; ++j) {
+                const float tj = ts[j];
+                const float4 u0 = *reinterpret_cast<const float4*>(s_up + (size_t)j * Nout + v * 8);
+                const float4 u1 = *reinterpret_cast<const float4*>(s_up + (size_t)j * Nout + v * 8 + 4);
+                f[0] = fmaf(tj, u0.x, f[0]); f[1] = fmaf(tj, u0.y, f[1]); f[2] = fmaf(tj, u0.z, f[2]); f[3] = fmaf(tj, u0.w, f[3]);
+                f[4] = fmaf(tj, u1.x, f[4]); f[5] = fmaf(tj, u1.y, f[5]); f[6] = fmaf(tj, u1.z, f[6]); f[7] = fmaf(tj, u1.w, f[7]);
             }
             *reinterpret_cast<uint4*>(yr + (size_t)v * 8) = pack8<T>(f);
         }

@@ -13,7 +13,13 @@ from typing import List, Optional
 import torch
 import torch.nn.functional as F
 
+import os
+
 from . import ops
+
+# 'k3' (default): one tmx_routed_linear_fwd launch per projection for all routed rows; 'cublas': two skinny cuBLAS GEMMs
+# per routed row (kept for A/B measurements: profiles/README.md).
+LORA_IMPL = os.environ.get("TMX_LORA_IMPL", "k3")
 
 _next_tag = [0]
 
@@ -102,6 +108,16 @@ class LoRARouting:
             return y
         if not (x.is_contiguous() and y.is_contiguous()):
             raise RuntimeError("LoRA routing needs contiguous activations")
+        if LORA_IMPL == "cublas":
+            seg = y.shape[-1] // nseg
+            for r, (d, u) in enumerate(zip(downs, ups)):
+                if d is None:
+                    continue
+                t = F.linear(x[r], d)                                         # [M, nseg*rank]
+                rank = d.shape[0] // nseg
+                for s_ in range(nseg):
+                    y[r, :, s_ * seg:(s_ + 1) * seg].addmm_(t[:, s_ * rank:(s_ + 1) * rank], u[s_ * seg:(s_ + 1) * seg].t())
+            return y
         return ops.routed_linear(x, None, downs, ups, nseg=nseg, out=y)
 
     def add_qkv_self(self, attn, x, qkv):
