@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Small-shape sweep of every tmx kernel for `compute-sanitizer --tool memcheck` (GPU box):
+    compute-sanitizer --tool memcheck --error-exitcode 3 python tools/sanitize_small.py
+Ragged shapes on purpose (partial tiles, odd row counts); results are also checked loosely so a wrong answer is not silent."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tweediemix_b200 import build, ops  # noqa: E402
+
+
+def main():
+    build.build()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, generator=g, device=dev)
+    bf = torch.bfloat16
+    # attention: partial q tile, partial kv tile, cross length 77, several heads / batches
+    for (B, H, Nq, Nk) in [(1, 1, 1, 1), (1, 2, 200, 77), (2, 3, 130, 129), (1, 1, 384, 256)]:
+        q, k, v = rnd(B, Nq, H * 64).to(bf), rnd(B, Nk, H * 64).to(bf), rnd(B, Nk, H * 64).to(bf)
+        o = ops.attention(q, k, v, H)
+        ref = torch.nn.functional.scaled_dot_product_attention(
+            q.view(B, Nq, H, 64).transpose(1, 2).float(), k.view(B, Nk, H, 64).transpose(1, 2).float(), v.view(B, Nk, H, 64).transpose(1, 2).float())
+        assert (o.float() - ref.transpose(1, 2).reshape(B, Nq, H * 64)).abs().max() < 3e-2
+    # GroupNorm: fused (NHWC 16-bit), two-pass (fp32), NCHW
+    for shape, dt, cl in [((2, 64, 5, 7), bf, True), ((3, 320, 9, 9), bf, True), ((1, 32, 1, 8), torch.float32, True), ((2, 64, 4, 6), bf, False)]:
+        x = rnd(*shape).to(dt)
+        if cl:
+            x = x.contiguous(memory_format=torch.channels_last)
+        y = ops.group_norm(x, torch.ones(shape[1], device=dev), torch.zeros(shape[1], device=dev), 32, 1e-5, silu=True)
+        ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float(), 32))
+        assert (y.float() - ref).abs().max() < 3e-2
+    # LayerNorm, fused residual + LayerNorm, residual add, GEGLU
+    x = rnd(3, 5, 64).to(bf)
+    ops.layer_norm(x, torch.ones(64, device=dev), torch.zeros(64, device=dev), 1e-5)
+    ops.residual_add_layer_norm(x.clone(), x, torch.ones(64, device=dev), torch.zeros(64, device=dev), 1e-5)
+    ops.residual_add(x, x)
+    ops.geglu(rnd(7, 3, 48).to(bf))
+    # k7 and its sharded halves
+    xl = rnd(2, 4, 8, 8)
+    eps = rnd(2, 4, 4, 8, 8).to(bf)
+    m = (torch.rand(3, 1, 8, 8, generator=g, device=dev) > 0.5).float()
+    ops.tweedie_blend_ddim(xl, eps, m, 0.3, 0.4, 0.8)
+    acc = torch.empty(2, 2, 4, 8, 8, device=dev)
+    ops.blend_partial(eps[:, 1:3].contiguous(), m, [1, 2], acc, 2)
+    ops.blend_finish(xl, acc, m, 0.3, 0.4, 0.8)
+    # k3: grouped GEMM with ragged M / Nout, LoRA deltas with an unrouted row
+    x = rnd(3, 130, 128).to(bf)
+    ws = [(rnd(136, 128) / 11).to(bf) for _ in range(3)]
+    y = ops.routed_linear(x, ws)
+    assert (y.float() - torch.stack([x[b].float() @ ws[b].float().t() for b in range(3)])).abs().max() < 5e-2
+    downs = [None] + [(rnd(4, 128) / 4).to(bf) for _ in range(2)]
+    ups = [None] + [(rnd(136, 4) * 0.05).to(bf) for _ in range(2)]
+    ops.routed_linear(x, None, downs, ups, nseg=1, out=y)
+    x2, y2 = rnd(2, 37, 64).to(bf), rnd(2, 37, 48).to(bf)
+    ops.routed_linear(x2, None, [None, (rnd(12, 64) / 4).to(bf)], [None, (rnd(48, 4) * 0.05).to(bf)], nseg=3, out=y2)
+    torch.cuda.synchronize()
+    print("sanitize_small: all kernels ran")
+
+
+if __name__ == "__main__":
+    main()
