@@ -21,6 +21,11 @@
 #include "tmx_common.cuh"
 #include <cuda.h>
 
+// The two-rows-per-warp LoRA kernel (lora_delta_kernel2) is the default; -DTMX_LORA_V1 selects the row-at-a-time one.
+#if !defined(TMX_LORA_V1) && !defined(TMX_LORA_V2)
+#define TMX_LORA_V2
+#endif
+
 namespace tmx {
 namespace k3 {
 
@@ -299,6 +304,93 @@ lora_delta_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_const
     }
 }
 
+// Same contract, two token rows per warp in flight: every shared-memory factor load feeds two rows (half the LDS
+// traffic of the row-at-a-time kernel) and the two dependent FMA chains interleave.
+template <typename T, int SR>
+__global__ void __launch_bounds__(kLoraWarps * 32, 1)
+lora_delta_kernel2(const T* __restrict__ x, T* __restrict__ y, const __grid_constant__ LoraPtrs ptrs,
+                   int M, int Kin, int Nout, int r, int seg_cols) {
+    extern __shared__ float lora_smem[];
+    const int b = blockIdx.y;
+    const T* down = reinterpret_cast<const T*>(ptrs.down[b]);
+    const T* up = reinterpret_cast<const T*>(ptrs.up[b]);
+    if (down == nullptr) return;
+    float* s_down = lora_smem;                                 // [SR][Kin]
+    float* s_up = lora_smem + (size_t)SR * Kin;                // [r][Nout]
+    __shared__ float s_t[kLoraWarps][2][16];
+    for (int i = threadIdx.x; i < SR * Kin / 8; i += blockDim.x) {
+        float f[8];
+        unpack8<T>(ld_keep(down + (size_t)i * 8), f);
+        *reinterpret_cast<float4*>(s_down + (size_t)i * 8) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(s_down + (size_t)i * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (int i = threadIdx.x; i < Nout * r / 8; i += blockDim.x) {
+        float f[8];
+        unpack8<T>(ld_keep(up + (size_t)i * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = i * 8 + e;
+            const int n = idx / r, j = idx - n * r;
+            s_up[(size_t)j * Nout + n] = f[e];
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec_in = Kin >> 3, nvec_out = Nout >> 3;
+    const int row0 = (blockIdx.x * kLoraWarps + warp) * kLoraRowsPerWarp;
+    for (int rr = 0; rr < kLoraRowsPerWarp; rr += 2) {
+        const int m0 = row0 + rr, m1 = m0 + 1;
+        if (m0 >= M) break;                                    // warp-uniform
+        const bool has1 = (rr + 1 < kLoraRowsPerWarp) && (m1 < M);
+        const T* x0 = x + ((size_t)b * M + m0) * Kin;
+        const T* x1 = x + ((size_t)b * M + (has1 ? m1 : m0)) * Kin;
+        float t0[SR], t1[SR];
+#pragma unroll
+        for (int q = 0; q < SR; ++q) { t0[q] = 0.f; t1[q] = 0.f; }
+        for (int v = lane; v < nvec_in; v += 32) {
+            float f0[8], f1[8];
+            unpack8<T>(ld_stream(x0 + (size_t)v * 8), f0);
+            unpack8<T>(ld_stream(x1 + (size_t)v * 8), f1);
+#pragma unroll
+            for (int q = 0; q < SR; ++q) {
+                const float4 d0 = *reinterpret_cast<const float4*>(s_down + (size_t)q * Kin + v * 8);
+                const float4 d1 = *reinterpret_cast<const float4*>(s_down + (size_t)q * Kin + v * 8 + 4);
+                t0[q] = fmaf(f0[0], d0.x, fmaf(f0[1], d0.y, fmaf(f0[2], d0.z, fmaf(f0[3], d0.w,
+                        fmaf(f0[4], d1.x, fmaf(f0[5], d1.y, fmaf(f0[6], d1.z, fmaf(f0[7], d1.w, t0[q]))))))));
+                t1[q] = fmaf(f1[0], d0.x, fmaf(f1[1], d0.y, fmaf(f1[2], d0.z, fmaf(f1[3], d0.w,
+                        fmaf(f1[4], d1.x, fmaf(f1[5], d1.y, fmaf(f1[6], d1.z, fmaf(f1[7], d1.w, t1[q]))))))));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SR; ++q) { t0[q] = warp_sum(t0[q]); t1[q] = warp_sum(t1[q]); }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < SR; ++q) { s_t[warp][0][q] = t0[q]; s_t[warp][1][q] = t1[q]; }
+        }
+        __syncwarp();
+        T* y0 = y + ((size_t)b * M + m0) * Nout;
+        T* y1 = y + ((size_t)b * M + (has1 ? m1 : m0)) * Nout;
+        for (int v = lane; v < nvec_out; v += 32) {
+            const int so = ((v * 8) / seg_cols) * r;
+            float f0[8], f1[8];
+            unpack8<T>(ld_keep(y0 + (size_t)v * 8), f0);
+            unpack8<T>(ld_keep(y1 + (size_t)v * 8), f1);
+            for (int j = 0; j < r; ++j) {
+                const float a0 = s_t[warp][0][so + j], a1 = s_t[warp][1][so + j];
+                const float4 u0 = *reinterpret_cast<const float4*>(s_up + (size_t)j * Nout + v * 8);
+                const float4 u1 = *reinterpret_cast<const float4*>(s_up + (size_t)j * Nout + v * 8 + 4);
+                f0[0] = fmaf(a0, u0.x, f0[0]); f0[1] = fmaf(a0, u0.y, f0[1]); f0[2] = fmaf(a0, u0.z, f0[2]); f0[3] = fmaf(a0, u0.w, f0[3]);
+                f0[4] = fmaf(a0, u1.x, f0[4]); f0[5] = fmaf(a0, u1.y, f0[5]); f0[6] = fmaf(a0, u1.z, f0[6]); f0[7] = fmaf(a0, u1.w, f0[7]);
+                f1[0] = fmaf(a1, u0.x, f1[0]); f1[1] = fmaf(a1, u0.y, f1[1]); f1[2] = fmaf(a1, u0.z, f1[2]); f1[3] = fmaf(a1, u0.w, f1[3]);
+                f1[4] = fmaf(a1, u1.x, f1[4]); f1[5] = fmaf(a1, u1.y, f1[5]); f1[6] = fmaf(a1, u1.z, f1[6]); f1[7] = fmaf(a1, u1.w, f1[7]);
+            }
+            *reinterpret_cast<uint4*>(y0 + (size_t)v * 8) = pack8<T>(f0);
+            if (has1) *reinterpret_cast<uint4*>(y1 + (size_t)v * 8) = pack8<T>(f1);
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -321,12 +413,18 @@ static int launch_lora(const void* x, void* y, const LoraPtrs& ptrs, int B, int 
     dim3 grid((M + kLoraWarps * kLoraRowsPerWarp - 1) / (kLoraWarps * kLoraRowsPerWarp), B);
     const int seg_cols = Nout / nseg;
     switch (SR) {
+#ifdef TMX_LORA_V2
+#define lora_delta_kernel lora_delta_kernel2
+#endif
         case 4:  lora_delta_kernel<T, 4><<<grid, kLoraWarps * 32, smem, st>>>((const T*)x, (T*)y, ptrs, M, Kin, Nout, r, seg_cols); break;
         case 8:  lora_delta_kernel<T, 8><<<grid, kLoraWarps * 32, smem, st>>>((const T*)x, (T*)y, ptrs, M, Kin, Nout, r, seg_cols); break;
         case 12: lora_delta_kernel<T, 12><<<grid, kLoraWarps * 32, smem, st>>>((const T*)x, (T*)y, ptrs, M, Kin, Nout, r, seg_cols); break;
         case 16: lora_delta_kernel<T, 16><<<grid, kLoraWarps * 32, smem, st>>>((const T*)x, (T*)y, ptrs, M, Kin, Nout, r, seg_cols); break;
         default: set_error("routed_linear: nseg * r = %d unsupported (4, 8, 12 or 16)", SR); return TMX_ESHAPE;
     }
+#ifdef TMX_LORA_V2
+#undef lora_delta_kernel
+#endif
     return check_cuda(cudaGetLastError(), "lora_delta_kernel launch");
 }
 
@@ -343,7 +441,8 @@ int routed_init() {
     }
     TMX_CUDA(cudaFuncSetAttribute(routed_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     TMX_CUDA(cudaFuncSetAttribute(routed_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-#define K3_ATTR(T, SR) TMX_CUDA(cudaFuncSetAttribute(lora_delta_kernel<T, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoraSmemMax))
+#define K3_ATTR(T, SR) TMX_CUDA(cudaFuncSetAttribute(lora_delta_kernel<T, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoraSmemMax)); \
+                       TMX_CUDA(cudaFuncSetAttribute(lora_delta_kernel2<T, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoraSmemMax))
     K3_ATTR(__half, 4); K3_ATTR(__half, 8); K3_ATTR(__half, 12); K3_ATTR(__half, 16);
     K3_ATTR(__nv_bfloat16, 4); K3_ATTR(__nv_bfloat16, 8); K3_ATTR(__nv_bfloat16, 12); K3_ATTR(__nv_bfloat16, 16);
 #undef K3_ATTR
