@@ -316,16 +316,9 @@ gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
 #pragma unroll
         for (int u = 0; u < 8; ++u) q[u] = qn[u];
     }
-#if defined(TMX_GN_EXPERIMENT_STAGE) && TMX_GN_EXPERIMENT_STAGE == 1
-    if (S[0] == 123.456f) y[0] = x[0];
-    return;
-#endif
     gn_cta_group_sums(sh, S, SS, C, CV, RY, G, cpg, tx, ty,
                       [&](int g, float s, float ss) { part[((size_t)n * G + g) * P + blockIdx.x] = make_float2(s, ss); });
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // blockDim.x is a multiple of 32 (plan_fused)
-#if defined(TMX_GN_EXPERIMENT_STAGE) && TMX_GN_EXPERIMENT_STAGE == 2
-    return;
-#endif
     // ---- sense-reversing barrier over the P CTAs of batch row n (arrival counter re-armed by the last arriver,
     // generation word read at kernel entry), then EVERY CTA folds the P partials itself in the same fixed order
     // (bit-identical statistics everywhere, and no finalise -> publish -> re-read round trips).
@@ -338,7 +331,6 @@ gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
     }
     __threadfence();
     __syncthreads();
-#ifndef TMX_GN_EXPERIMENT_NOBARRIER
     if (threadIdx.x == 0) {
         if (atomicAdd(cnt, 1u) == (unsigned)(P - 1)) {                   // last arriver: re-arm the counter, open the barrier
             *cnt = 0u;
@@ -356,7 +348,6 @@ gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
             }
         }
     }
-#endif
     __syncthreads();
     {
         const float inv = 1.f / ((float)HW * (float)cpg);
@@ -409,12 +400,7 @@ gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float v = fmaf(f[j], a[j], b[j]);
-            
-#if defined(TMX_GN_EXPERIMENT_STAGE) && TMX_GN_EXPERIMENT_STAGE == 3
-            f[j] = v;
-#else
             f[j] = act ? silu_for<T>(v) : v;
-#endif
         }
         st_stream(ycol + (size_t)rr * C, pack8<T>(f));
     }
