@@ -216,3 +216,41 @@ def test_assign_rows():
     assert [assign_rows(2, 4, r) for r in range(4)] == [[0], [1], [], []]
     assert [assign_rows(9, 4, r) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7, 8], []]
     assert assign_rows(4, 1, 0) == [0, 1, 2, 3]
+
+
+@pytest.mark.parametrize("variant", ["custom", "lora"])
+def test_product_host_path_matches_reference_run(monkeypatch, variant, golden_dir):
+    """The PRODUCT's Tweediemix / hook layer / U-Net wiring (tmx kernels replaced by the plain-PyTorch stand-ins, fp32,
+    CPU) against the latents the REFERENCE's own unmodified init_fusion + denoise_step produced step by step
+    (tests/golden/make_golden_sampler.py): config 1 (256x256, 5 steps, custom) and the 10-step LoRA run with t_stop.
+    Tolerance 1e-3 max-abs — the north star's end-to-end bound; fp32 lands at ~1e-5."""
+    import argparse
+    import os
+    from tweediemix_b200.fusion_sampling import FusionComponents, Tweediemix
+    from tweediemix_b200.schedule import DDIMSchedule
+    fake_ops.install(monkeypatch)
+    lora = variant == "lora"
+    gold = torch.load(os.path.join(golden_dir, "sampler_lora_n10.pt" if lora else "sampler_custom_n5.pt"))
+    m = gold["meta"]
+    ref_unet = synth.make_base_unet(RCFG, m["base_seed"])
+    extra = [make_lora_set(ref_unet, s) for s in m["lora_seeds"]] if lora else \
+            [synth.make_concept_unet(ref_unet, s) for s in m["concept_seeds"]]
+    # same construction as _product_sampler, with the golden run's text seed / step counts
+    prod = _product_sampler(ref_unet, extra, lora, m["n"], m["res"])
+    text, single = synth.make_text(RCFG, K, m["text_seed"])
+    ns = argparse.Namespace(guidance_scale=m["guidance_scale"], n_timesteps=m["n"], t_cond=m["t_cond"], t_stop=m.get("t_stop"),
+                            resampling_steps=m["resampling_steps"], jumping_steps=m["jumping_steps"], resolution_h=m["res"],
+                            resolution_w=m["res"], crops_coords_top_left_h=0, crops_coords_top_left_w=0, seed=3821, output_path=".",
+                            seg_concepts="a cat+a dog", seg_gpu=0)
+    comp = FusionComponents(unet=prod.unet, concept_unets=[getattr(prod, f"unet_{i}") for i in range(K)], text_embeds=text,
+                            text_embeds_single=single, scheduler=DDIMSchedule(), masks=gold["masks"].clone())
+    model = Tweediemix(ns, comp, variant=variant, use_cuda_graphs=False)
+    if lora:
+        model.init_fusion(int(m["n"] * m["t_cond"]), int(m["n"] * m["t_stop"]))
+    else:
+        model.init_fusion(int(m["n"] * m["t_cond"]))
+    got = []
+    model.sample_loop(gold["x0"].clone(), callback=lambda i, t, x: got.append(x.clone()))
+    assert len(got) == len(gold["xs"])
+    for i, (a, b) in enumerate(zip(got, gold["xs"])):
+        assert (a - b).abs().max().item() < 1e-3, f"step {i}: {(a - b).abs().max().item()}"
