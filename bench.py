@@ -187,15 +187,8 @@ def run_ours(args):
     from tweediemix_b200.synthetic import make_components, make_text
     from tweediemix_b200.unet import UNetConfig
 
-    group_size = min(world, K_CONCEPTS + 1)
-    n_groups = max(world // group_size, 1)
-    my_group = rank // group_size
-    pg = None
-    if world > 1:
-        for gi in range(n_groups):                    # every rank must create every group
-            g = dist.new_group(list(range(gi * group_size, (gi + 1) * group_size)))
-            if gi == my_group:
-                pg = g
+    from tweediemix_b200.fusion_sampling import make_concept_groups
+    group_size, n_groups, my_group, pg = make_concept_groups(world, rank, K_CONCEPTS + 1)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     masks_host = load_region_masks(MASK_DIR, MASK_NAMES, 128, 128).pin_memory()
     comp = make_components(K_CONCEPTS, args.variant, seed=args.seed, device=dev, dtype=dtype, masks=masks_host)

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, lora, out_dir):
+def _worker(rank, world, port, lora, out_dir, max_group=None):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -38,11 +38,14 @@ def _worker(rank, world, port, lora, out_dir):
         ref_unet = synth.make_base_unet(T.RCFG, 1)
         extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(T.K)] if lora else \
                 [synth.make_concept_unet(ref_unet, 10 + i) for i in range(T.K)]
-        s = T._product_sampler(ref_unet, extra, lora, n, res, pg=dist.group.WORLD)
+        from tweediemix_b200.fusion_sampling import make_concept_groups
+        gsize, n_groups, my_group, pg = make_concept_groups(world, rank, T.K + 1, max_group)
+        s = T._product_sampler(ref_unet, extra, lora, n, res, pg=pg)
         s.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else s.init_fusion(int(n * 0.2))
-        torch.manual_seed(7)
+        torch.manual_seed(7 + my_group)                      # every image group samples its own image
         x = s.sample_loop(torch.randn(1, 4, res // 8, res // 8))
-        torch.save({"x": x, "rows": s.n_forward_rows}, os.path.join(out_dir, f"rank{rank}.pt"))
+        torch.save({"x": x, "rows": s.n_forward_rows, "group": my_group, "gsize": gsize, "n_groups": n_groups},
+                   os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -71,3 +74,36 @@ def test_concept_parallel_two_ranks_equals_single(tmp_path, monkeypatch, lora):
     # the sharded path evaluates the CFG / blend in its linear form (fp32): equal up to round-off
     assert (r0["x"] - want).abs().max().item() < 2e-4
     assert r0["rows"] + r1["rows"] == single.n_forward_rows      # every batch row computed exactly once
+
+
+def test_two_image_groups_of_two_ranks(tmp_path, monkeypatch):
+    """world_size 4 with groups capped at 2 ranks = the shape of the 8-GPU run (two 4-rank groups): each group
+    block-distributes the K+1 rows of ITS image, all-reduces inside the group only, and reproduces the single-process
+    latent of that image; the two groups never exchange data."""
+    world = 4
+    mp.spawn(_worker, args=(world, _free_port(), False, str(tmp_path), 2), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f"rank{k}.pt") for k in range(world)]
+    assert [x["group"] for x in r] == [0, 0, 1, 1] and all(x["gsize"] == 2 and x["n_groups"] == 2 for x in r)
+    assert torch.equal(r[0]["x"], r[1]["x"]) and torch.equal(r[2]["x"], r[3]["x"])
+    assert not torch.equal(r[0]["x"], r[2]["x"])
+
+    sys.path.insert(0, HERE)
+    import fake_ops
+    import test_host_logic as T
+    from oracle import synth
+    fake_ops.install(monkeypatch)
+    n, res = 5, 128
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = [synth.make_concept_unet(ref_unet, 10 + i) for i in range(T.K)]
+    for g in range(2):
+        single = T._product_sampler(ref_unet, extra, False, n, res)
+        single.init_fusion(int(n * 0.2))
+        torch.manual_seed(7 + g)
+        want = single.sample_loop(torch.randn(1, 4, res // 8, res // 8))
+        assert (r[2 * g]["x"] - want).abs().max().item() < 2e-4
+        assert r[2 * g]["rows"] + r[2 * g + 1]["rows"] == single.n_forward_rows
+
+
+def test_make_concept_groups_single_process():
+    from tweediemix_b200.fusion_sampling import make_concept_groups
+    assert make_concept_groups(1, 0, 4) == (1, 1, 0, None)

@@ -85,6 +85,25 @@ def assign_rows(n_rows: int, group_size: int, rank: int) -> List[int]:
     return list(range(min(n_rows, rank * q), min(n_rows, (rank + 1) * q)))
 
 
+def make_concept_groups(world: int, rank: int, n_rows: int, max_group: Optional[int] = None):
+    """Concept-parallel process groups.  The ``n_rows`` = K+1 batch rows of one image are the only work that
+    shards, so ranks form ``n_groups = world // G`` groups of ``G = min(world, n_rows[, max_group])`` ranks; a group
+    block-distributes the rows of ONE image and all-reduces once per step, different groups sample different images.
+    Every rank creates every group (``dist.new_group`` is collective).  Returns (G, n_groups, my_group, my process group or
+    None when G == 1 or world == 1)."""
+    group_size = max(1, min(world, n_rows, max_group if max_group else world))
+    n_groups = max(world // group_size, 1)
+    my_group = min(rank // group_size, n_groups - 1)
+    pg = None
+    if world > 1 and group_size > 1:
+        import torch.distributed as dist
+        for gi in range(n_groups):
+            g = dist.new_group(list(range(gi * group_size, (gi + 1) * group_size)))
+            if gi == my_group and rank < n_groups * group_size:
+                pg = g
+    return group_size, n_groups, my_group, pg
+
+
 class Tweediemix(nn.Module):
     def __init__(self, config, components: Optional[FusionComponents] = None, *, variant: str = "custom",
                  use_cuda_graphs: Optional[bool] = None, process_group=None, gate: Optional[int] = None,
