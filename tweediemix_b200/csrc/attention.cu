@@ -311,7 +311,8 @@ template <int HV> struct AttnCfg {
 };
 constexpr int kTmemCols = 512;
 constexpr int kBars = 6 * kSlots + 2 * kQBufs * kSlots + 4 * kStages;
-constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages) * kTileBytes + kBars * 8 + 16 + 2 * kSlots * 2 * kBM * 4;
+constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages) * kTileBytes + kBars * 8 + 16 + 2 * kSlots * 2 * kBM * 4 /*l_xchg*/
+                           + 2 * kSlots * 2 * kBM * 4 /*m_xchg (HV == 2 with -DTMX_ATTN_HV2_XCHG)*/;
 
 // One scheduling step of a CTA: query tile `qt` (and qt+1 when nslots == 2) of head h, batch b.
 struct Step { int b, h, qt, nslots; };
@@ -357,6 +358,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t v_empty = v_full + 8 * ST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBars);
     float* l_xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [2 step parities][kSlots][2 halves][kBM] partial row sums
+    float* m_xchg = l_xchg + 2 * kSlots * 2 * kBM;             // [2 tile parities][kSlots][2 halves][kBM] half-row maxima (HV2_XCHG)
+    (void)m_xchg;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -564,7 +567,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tc_fence_after();
                 uint32_t s[COLS];
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#ifndef TMX_ATTN_EXPERIMENT_NOMAX
+#if !defined(TMX_ATTN_EXPERIMENT_NOMAX) && !defined(TMX_ATTN_HV2_XCHG)
                 if constexpr (HV == 2) {
                     // the other half of the row: only its maximum is needed
                     const uint32_t t_other = t_row + (half ^ 1) * COLS;
@@ -601,7 +604,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     mx0 = fmaxf(mx0, __uint_as_float(s[c])); mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
                     mx2 = fmaxf(mx2, __uint_as_float(s[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
                 }
-                const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+                float row_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+#ifdef TMX_ATTN_HV2_XCHG
+                // (NOT YET RUN ON A GPU — opt-in build.)  HV == 2 without the redundant read of the other half: the two threads
+                // of a row swap their half-row maxima through shared memory.  Buffers alternate with the tile parity, so ONE
+                // 64-thread named barrier per tile orders both the hand-over and the reuse two tiles later.
+                if constexpr (HV == 2) {
+                    float* mxb = m_xchg + ((n & 1u) * kSlots + w) * 2 * kBM;
+                    mxb[half * kBM + row] = row_max;
+                    asm volatile("bar.sync %0, 64;" :: "r"(3 + w * 4 + quarter) : "memory");
+                    row_max = fmaxf(row_max, mxb[(half ^ 1) * kBM + row]);
+                }
+#endif
+                const float m_tile = row_max * scale_log2;
                 // lazy rescale: move the reference only when the max grew by more than 2^8
                 const bool bump = m_tile > m_ref + kRescaleThreshold;
                 const float m_new = bump ? m_tile : m_ref;
