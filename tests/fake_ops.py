@@ -103,10 +103,11 @@ def _mw(masks, weights, K, like):
 
 def tweedie_blend_ddim(x, eps, masks, a_t, a_next, g, *, is_last=False, weights=None, out=None, x0_out=None,
                        ref_rounding=False):
-    C, H, W = x.shape[1:]
-    e = eps.reshape(-1, C, H, W).float()
-    K = e.shape[0] - 1
-    res, x0 = sm.fused_step(x, e, _mw(masks, weights, K, x), a_t, a_next, g, is_last=is_last)
+    imgs, C, H, W = x.shape
+    e = eps.reshape(imgs, -1, C, H, W).float()                 # [imgs, K+1, C, H, W], image-major like the real op
+    K = e.shape[1] - 1
+    res, x0 = zip(*[sm.fused_step(x[i:i + 1], e[i], _mw(masks, weights, K, x), a_t, a_next, g, is_last=is_last) for i in range(imgs)])
+    res, x0 = torch.cat(res), torch.cat(x0)
     if x0_out is not None:
         x0_out.copy_(x0)
     if out is not None:
@@ -131,7 +132,10 @@ def blend_partial(eps_rows, masks, row_ids, acc, imgs=1, *, K=None, weights=None
 def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_out=None, K=None, weights=None):
     K = masks.shape[0] if K is None else K
     M = _mw(masks, weights, K, x).sum(dim=0, keepdim=True).expand(1, 1, *x.shape[2:])
-    res, x0 = sm.blend_finish(x, acc[:, 0], acc[:, 1], M, a_t, a_next, g, is_last=is_last)
+    res, x0 = zip(*[sm.blend_finish(x[i:i + 1], acc[i:i + 1, 0], acc[i:i + 1, 1], M, a_t, a_next, g, is_last=is_last) for i in range(x.shape[0])])
+    res, x0 = torch.cat(res), torch.cat(x0)
+    if x0_out is not None:
+        x0_out.copy_(x0)
     if out is not None:
         out.copy_(res)
         return out

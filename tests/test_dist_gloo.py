@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, lora, out_dir, max_group=None):
+def _worker(rank, world, port, lora, out_dir, max_group=None, n_imgs=1, k=None):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -35,15 +35,16 @@ def _worker(rank, world, port, lora, out_dir, max_group=None):
         from oracle import synth
         from oracle.hooks_ref import make_lora_set
         n, res = 5, 128
+        k = T.K if k is None else k
         ref_unet = synth.make_base_unet(T.RCFG, 1)
-        extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(T.K)] if lora else \
-                [synth.make_concept_unet(ref_unet, 10 + i) for i in range(T.K)]
+        extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(k)] if lora else \
+                [synth.make_concept_unet(ref_unet, 10 + i) for i in range(k)]
         from tweediemix_b200.fusion_sampling import make_concept_groups
-        gsize, n_groups, my_group, pg = make_concept_groups(world, rank, T.K + 1, max_group)
-        s = T._product_sampler(ref_unet, extra, lora, n, res, pg=pg)
+        gsize, n_groups, my_group, pg = make_concept_groups(world, rank, (k + 1) * n_imgs, max_group)
+        s = T._product_sampler(ref_unet, extra, lora, n, res, pg=pg, k=k)
         s.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else s.init_fusion(int(n * 0.2))
-        torch.manual_seed(7 + my_group)                      # every image group samples its own image
-        x = s.sample_loop(torch.randn(1, 4, res // 8, res // 8))
+        torch.manual_seed(7 + my_group)                      # every image group samples its own image(s)
+        x = s.sample_loop(torch.randn(n_imgs, 4, res // 8, res // 8))
         torch.save({"x": x, "rows": s.n_forward_rows, "group": my_group, "gsize": gsize, "n_groups": n_groups},
                    os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
@@ -102,6 +103,32 @@ def test_two_image_groups_of_two_ranks(tmp_path, monkeypatch):
         want = single.sample_loop(torch.randn(1, 4, res // 8, res // 8))
         assert (r[2 * g]["x"] - want).abs().max().item() < 2e-4
         assert r[2 * g]["rows"] + r[2 * g + 1]["rows"] == single.n_forward_rows
+
+
+@pytest.mark.parametrize("world,k,n_imgs", [(3, 3, 2), (2, 8, 1)])
+def test_units_of_several_images_over_uneven_ranks(tmp_path, monkeypatch, world, k, n_imgs):
+    """(image, prompt row) units split over ranks that do not divide them: 2 images x 4 rows over 3 ranks (3/3/2, rank 1
+    holds rows of BOTH images) and K = 8 (9 rows over 2 ranks, 5/4) — the shape of BASELINE configs[3] (9 rows x 4 images
+    over 8 ranks).  Every rank ends with the latents of the single-process run."""
+    mp.spawn(_worker, args=(world, _free_port(), False, str(tmp_path), None, n_imgs, k), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f"rank{q}.pt") for q in range(world)]
+    for q in range(1, world):
+        assert torch.equal(r[0]["x"], r[q]["x"])
+    sys.path.insert(0, HERE)
+    import fake_ops
+    import test_host_logic as T
+    from oracle import synth
+    fake_ops.install(monkeypatch)
+    n, res = 5, 128
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = [synth.make_concept_unet(ref_unet, 10 + i) for i in range(k)]
+    single = T._product_sampler(ref_unet, extra, False, n, res, k=k)
+    single.init_fusion(int(n * 0.2))
+    torch.manual_seed(7)
+    want = single.sample_loop(torch.randn(n_imgs, 4, res // 8, res // 8))
+    assert (r[0]["x"] - want).abs().max().item() < 1e-3
+    assert sum(x["rows"] for x in r) == single.n_forward_rows
+    assert max(x["rows"] for x in r) - min(x["rows"] for x in r) <= single.n_forward_rows // (world * 4) + 5   # balanced
 
 
 def test_make_concept_groups_single_process():

@@ -126,13 +126,18 @@ def _namespace(n, res, lora):
                               seg_concepts="a+b", seg_gpu=0)
 
 
-def _product_sampler(ref_unet, donors_or_loras, lora, n, res, pg=None):
+def _masks_for(k, h, w):
+    """The reference's shipped mask pair (+ background) for K == 3, a stripe partition otherwise."""
+    return synth.fixture_masks(h, w) if k == 3 else synth.stripe_masks(k, h, w)
+
+
+def _product_sampler(ref_unet, donors_or_loras, lora, n, res, pg=None, k=K, **kw):
     from tweediemix_b200.fusion_sampling import FusionComponents, Tweediemix
     from tweediemix_b200.schedule import DDIMSchedule
     from tweediemix_b200.synthetic import SparseUNet
     prod = product_unet(ref_unet)
-    text, single = synth.make_text(RCFG, K, 77)
-    masks = synth.fixture_masks(res // 8, res // 8)
+    text, single = synth.make_text(RCFG, k, 77)
+    masks = _masks_for(k, res // 8, res // 8)
     if lora:
         from tweediemix_b200.model_lora import LoRALinearLayer
         donors = []
@@ -153,15 +158,17 @@ def _product_sampler(ref_unet, donors_or_loras, lora, n, res, pg=None):
     comp = FusionComponents(unet=prod, concept_unets=donors, text_embeds=text, text_embeds_single=single,
                             scheduler=DDIMSchedule(), masks=masks)
     return Tweediemix(_namespace(n, res, lora), comp, variant="lora" if lora else "custom",
-                      use_cuda_graphs=False, process_group=pg)
+                      use_cuda_graphs=False, process_group=pg, **kw)
 
 
-def _oracle_sampler(ref_unet, donors_or_loras, lora, n, res):
-    text, single = synth.make_text(RCFG, K, 77)
-    masks = synth.fixture_masks(res // 8, res // 8)
+def _oracle_sampler(ref_unet, donors_or_loras, lora, n, res, k=K):
+    """The oracle sampler; for K != 3 the routing gate is generalised from the reference's literal 4 (utils_custom.py:61-62,
+    utils_lora.py:63) to K + 1, which is what the product does by default."""
+    text, single = synth.make_text(RCFG, k, 77)
+    masks = _masks_for(k, res // 8, res // 8)
     cfg = RefConfig(n_timesteps=n, resolution_h=res, resolution_w=res, t_stop=0.8 if lora else None, resampling_steps=2)
-    s = TweediemixRef(ref_unet, text, single, masks, cfg, K, lora=lora, run_jump=False)
-    (register_lora_ref if lora else register_custom_ref)(ref_unet, donors_or_loras, s.hook_gate_window(), K)
+    s = TweediemixRef(ref_unet, text, single, masks, cfg, k, lora=lora, run_jump=False)
+    (register_lora_ref if lora else register_custom_ref)(ref_unet, donors_or_loras, s.hook_gate_window(), k, gate=k + 1)
     return s
 
 
@@ -214,8 +221,12 @@ def test_assign_rows():
     assert [assign_rows(4, 2, r) for r in range(2)] == [[0, 1], [2, 3]]
     assert [assign_rows(4, 4, r) for r in range(4)] == [[0], [1], [2], [3]]
     assert [assign_rows(2, 4, r) for r in range(4)] == [[0], [1], [], []]
-    assert [assign_rows(9, 4, r) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7, 8], []]
+    assert [assign_rows(9, 4, r) for r in range(4)] == [[0, 1, 2], [3, 4], [5, 6], [7, 8]]      # balanced: no idle rank
+    assert [len(assign_rows(36, 8, r)) for r in range(8)] == [5, 5, 5, 5, 4, 4, 4, 4]           # configs[3]: 9 rows x 4 images
     assert assign_rows(4, 1, 0) == [0, 1, 2, 3]
+    from tweediemix_b200.fusion_sampling import assign_units
+    assert assign_units(2, 4, 2, 1) == [(1, 0), (1, 1), (1, 2), (1, 3)]                         # image-major units
+    assert assign_units(4, 9, 8, 0) == [(0, 0), (0, 1), (0, 2), (0, 3), (0, 4)]
 
 
 @pytest.mark.parametrize("variant", ["custom", "lora"])

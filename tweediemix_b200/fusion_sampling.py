@@ -29,6 +29,7 @@ them the way the reference constructor does.
 from __future__ import annotations
 
 import argparse
+import copy
 import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
@@ -42,6 +43,14 @@ from .masks import load_region_masks
 from .schedule import DDIMSchedule
 
 opt = None          # module-global parsed flags, like the reference (read by compute_time_ids)
+
+
+def save_image(img: torch.Tensor, path: str) -> None:
+    """[3,H,W] in [0,1] -> 8-bit RGB file (what ``T.ToPILImage()(img).save(path)`` writes, ``fusion_sampling.py:455,522``)."""
+    import numpy as np
+    from PIL import Image
+    arr = (img.detach().float().cpu().clamp(0, 1) * 255.0).to(torch.uint8).permute(1, 2, 0).numpy()   # ToPILImage: mul(255).byte()
+    Image.fromarray(np.ascontiguousarray(arr)).save(path)
 
 
 def compute_time_ids(config=None):
@@ -63,26 +72,42 @@ class FusionComponents:
 
 
 class _RowSet:
-    """Static device buffers of one phase: which prompt rows enter the U-Net, and (concept-parallel)
-    which of them this rank owns."""
+    """Static device buffers of one phase.  A *unit* is one (image, prompt row) pair = one batch row of the U-Net; this
+    rank owns the units ``local_units`` (image-major, so the rows of one image are contiguous in its eps tensor)."""
 
-    def __init__(self, name, ehs, pooled, time_ids, local_ids, n_rows, latent_shape, dtype, device):
-        self.name, self.n_rows, self.local_ids = name, n_rows, list(local_ids)
-        self.ehs = ehs[self.local_ids].to(device=device, dtype=dtype).contiguous() if self.local_ids else None
-        self.pooled = pooled[self.local_ids].to(device=device, dtype=dtype).contiguous() if self.local_ids else None
-        self.time_ids = time_ids.repeat(len(self.local_ids), 1).to(device) if self.local_ids else None
-        self.latent = torch.empty((len(self.local_ids),) + tuple(latent_shape[1:]), dtype=dtype, device=device) if self.local_ids else None
-        self.graphs = {}          # routed flag -> (CUDAGraph, eps tensor)
+    def __init__(self, name, ehs, pooled, time_ids, local_units, n_rows, n_imgs, latent_shape, dtype, device):
+        self.name, self.n_rows, self.n_imgs = name, n_rows, n_imgs
+        self.local_units = list(local_units)
+        self.local_ids = [r for _, r in self.local_units]            # prompt row of every local unit
+        self.local_imgs = [i for i, _ in self.local_units]
+        n = len(self.local_units)
+        self.ehs = ehs[self.local_ids].to(device=device, dtype=dtype).contiguous() if n else None
+        self.pooled = pooled[self.local_ids].to(device=device, dtype=dtype).contiguous() if n else None
+        self.time_ids = time_ids.repeat(n, 1).to(device) if n else None
+        self.latent = torch.empty((n,) + tuple(latent_shape[1:]), dtype=dtype, device=device) if n else None
+        self.img_index = torch.tensor(self.local_imgs, dtype=torch.long, device=device) if n and n_imgs > 1 else None
+        self.graphs = {}          # routed flag -> (CUDAGraph, eps tensor, launches per replay)
 
     def cond(self):
         return {"time_ids": self.time_ids, "text_embeds": self.pooled}
 
+    def rows_of_image(self, img: int):
+        """(first local index, prompt rows) of this rank's units of image ``img`` (contiguous by construction)."""
+        idx = [j for j, i in enumerate(self.local_imgs) if i == img]
+        return (idx[0] if idx else 0), [self.local_ids[j] for j in idx]
+
 
 def assign_rows(n_rows: int, group_size: int, rank: int) -> List[int]:
-    """Block distribution of batch rows over the ranks of a concept-parallel group: rank r owns rows
-    [r*q, (r+1)*q) with q = ceil(n_rows / group_size); trailing ranks may own nothing."""
-    q = -(-n_rows // group_size)
-    return list(range(min(n_rows, rank * q), min(n_rows, (rank + 1) * q)))
+    """Balanced contiguous distribution of ``n_rows`` work units over the ranks of a concept-parallel group: the first
+    ``n_rows % group_size`` ranks own one unit more; with fewer units than ranks the trailing ranks own nothing."""
+    q, rem = divmod(n_rows, group_size)
+    lo = rank * q + min(rank, rem)
+    return list(range(lo, lo + q + (1 if rank < rem else 0)))
+
+
+def assign_units(n_imgs: int, n_rows: int, group_size: int, rank: int) -> List[Tuple[int, int]]:
+    """(image, prompt row) units of this rank: the ``n_imgs * n_rows`` units, image-major, split by ``assign_rows``."""
+    return [divmod(u, n_rows) for u in assign_rows(n_imgs * n_rows, group_size, rank)]
 
 
 def make_concept_groups(world: int, rank: int, n_rows: int, max_group: Optional[int] = None):
@@ -107,8 +132,9 @@ def make_concept_groups(world: int, rank: int, n_rows: int, max_group: Optional[
 class Tweediemix(nn.Module):
     def __init__(self, config, components: Optional[FusionComponents] = None, *, variant: str = "custom",
                  use_cuda_graphs: Optional[bool] = None, process_group=None, gate: Optional[int] = None,
-                 ref_rounding: bool = False):
+                 ref_rounding: bool = False, mask_provider=None):
         super().__init__()
+        self.mask_provider = mask_provider          # callable(image_path, seg_concepts, h, w) -> [K,1,h,w]; replaces the os.system hand-off
         if variant not in ("custom", "lora"):
             raise ValueError("variant must be 'custom' or 'lora'")
         self.config = config
@@ -130,7 +156,9 @@ class Tweediemix(nn.Module):
         self.num_routed_concepts = len(components.concept_unets)
 
         # fusion_sampling.py:212-218 — N_ts is read BEFORE set_timesteps; the cumprod table gets a 1.0 prepended
-        self.scheduler = components.scheduler
+        # (the caller's scheduler object is left untouched: a private copy takes the reference's in-place edits, so a
+        # second Tweediemix built from the same components sees the same table)
+        self.scheduler = copy.deepcopy(components.scheduler)
         n_ts = len(self.scheduler.timesteps)
         self.scheduler.set_timesteps(config.n_timesteps, device=self.device)
         self.skip = n_ts // config.n_timesteps
@@ -151,6 +179,7 @@ class Tweediemix(nn.Module):
         self._rowsets = {}
         self._t_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._acc = None
+        self._hook_t = None           # the time the hooks were last told (register_time): decides routing, not the forward's t
         self.n_forward_rows = 0
         self.t_stop_cur = None
 
@@ -181,40 +210,50 @@ class Tweediemix(nn.Module):
         self._rowsets.clear()
 
     # ------------------------------------------------------------------ row sets / U-Net forward
-    def _rowset(self, name: str, like: torch.Tensor) -> _RowSet:
-        rs = self._rowsets.get(name)
-        if rs is not None:
-            return rs
+    def _prompt_rows(self, name: str):
         E, P = self.text_embeds
         if name == "fused":                   # :325-336  [uncond, c_1 .. c_K]
-            ehs, pool = torch.cat([E[0:1], E[2:]]), torch.cat([P[0:1], P[2:]])
-        elif name == "start":                 # :347-359  [uncond, multi, single_1 .. single_{K-1}]
+            return torch.cat([E[0:1], E[2:]]), torch.cat([P[0:1], P[2:]])
+        if name == "start":                   # :347-359  [uncond, multi, single_1 .. single_{K-1}]
             Es, Ps = self.text_embeds_single
-            ehs, pool = torch.cat([E[0:1], E[1:2], Es[1:]]), torch.cat([P[0:1], P[1:2], Ps[1:]])
-        else:                                 # :362-366  [uncond, multi]
-            ehs, pool = E[:2], P[:2]
+            return torch.cat([E[0:1], E[1:2], Es[1:]]), torch.cat([P[0:1], P[1:2], Ps[1:]])
+        return E[:2], P[:2]                   # :362-366  [uncond, multi]
+
+    def _rowset(self, name: str, like: torch.Tensor) -> _RowSet:
+        n_imgs = like.shape[0]
+        rs = self._rowsets.get((name, n_imgs))
+        if rs is not None:
+            return rs
+        ehs, pool = self._prompt_rows(name)
         n = ehs.shape[0]
-        local = assign_rows(n, self.group_size, self.group_rank)
-        rs = _RowSet(name, ehs, pool, self.add_time_ids, local, n, like.shape, self.unet.dtype, self.device)
-        self._rowsets[name] = rs
+        units = assign_units(n_imgs, n, self.group_size, self.group_rank)
+        rs = _RowSet(name, ehs, pool, self.add_time_ids, units, n, n_imgs, like.shape, self.unet.dtype, self.device)
+        self._rowsets[(name, n_imgs)] = rs
         return rs
 
     def _unet_call(self, rs: _RowSet):
         return self.unet(rs.latent, self._t_dev, encoder_hidden_states=rs.ehs, added_cond_kwargs=rs.cond())["sample"]
 
     def _forward(self, rs: _RowSet, x: torch.Tensor, t: int) -> Optional[torch.Tensor]:
-        """eps of this rank's rows of ``rs`` at latent ``x`` / timestep ``t`` ([R_local,4,h,w]) or None."""
-        if not rs.local_ids:
+        """eps of this rank's units of ``rs`` at latents ``x`` [imgs,4,h,w] / timestep ``t`` ([R_local,4,h,w]) or None."""
+        if not rs.local_units:
             return None
-        self.n_forward_rows += len(rs.local_ids)
-        rs.latent.copy_(x.expand(len(rs.local_ids), -1, -1, -1))
+        self.n_forward_rows += len(rs.local_units)
+        if rs.img_index is None:
+            rs.latent.copy_(x.expand(len(rs.local_units), -1, -1, -1))
+        else:
+            rs.latent.copy_(x.index_select(0, rs.img_index))
         self._t_dev.fill_(float(t))
-        local = rs.local_ids if self.group_size > 1 else None
+        # the hooks route row r of a gate-sized batch; a rank that holds other rows (concept-parallel) or several
+        # images says which prompt row every batch row is
+        local = rs.local_ids if (self.group_size > 1 or rs.n_imgs > 1) else None
         for _, attn in self.unet.attention_modules():
             attn.local_rows = local
         if not self.use_cuda_graphs:
             return self._unet_call(rs)
-        routed = t in self._window
+        # key = the decision the hooks take: the REGISTERED time (not this forward's t, which differs inside the
+        # resampling loop and the jump) in the window; the batch-size half of the gate is fixed per row set
+        routed = self._hook_t in self._window
         hit = rs.graphs.get(routed)
         if hit is None:
             side = torch.cuda.Stream()
@@ -229,33 +268,35 @@ class Tweediemix(nn.Module):
                 out = self._unet_call(rs)
             per_replay = {k: v - before.get(k, 0) for k, v in ops.LAUNCHES.items() if v != before.get(k, 0)}
             ops.add_launches(per_replay, -1)          # capture itself launches nothing
+            ops.pin_graph_resources()                 # workspaces / cached K/V captured by address must outlive the graph
             hit = rs.graphs[routed] = (graph, out, per_replay)
         hit[0].replay()
         ops.add_launches(hit[2])
         return hit[1]
 
     # ------------------------------------------------------------------ the fused tail (k7)
-    def _blend(self, x, eps, rs: _RowSet, use_rows: int, masks, weights, a_t, a_next, is_last, out=None):
-        """CFG + Tweedie + (masked / weighted) blend + DDIM over rows [0, use_rows) of ``rs``.
-        ``eps`` holds this rank's rows.  Single GPU: one k7 launch.  Concept-parallel: partial ->
-        all-reduce -> finish."""
+    def _blend(self, x, eps, rs: _RowSet, use_rows: int, masks, weights, a_t, a_next, is_last, out=None, x0_out=None):
+        """CFG + Tweedie + (masked / weighted) blend + DDIM over prompt rows [0, use_rows) of ``rs`` for every image.
+        ``eps`` holds this rank's units (image-major).  Single GPU: one k7 launch.  Concept-parallel: partial ->
+        ONE all-reduce -> finish."""
         g = float(self.config.guidance_scale)
         K = use_rows - 1
+        imgs = x.shape[0]
         if self.group_size == 1:
-            e = eps[:use_rows]
+            e = eps.reshape(imgs, rs.n_rows, *eps.shape[1:])
+            if use_rows != rs.n_rows:
+                e = e[:, :use_rows].contiguous() if imgs > 1 else e[:, :use_rows]
             return ops.tweedie_blend_ddim(x, e, masks, a_t, a_next, g, is_last=is_last, weights=weights, out=out,
-                                          ref_rounding=self.ref_rounding)
+                                          x0_out=x0_out, ref_rounding=self.ref_rounding)
         import torch.distributed as dist
-        if self._acc is None or self._acc.shape[2:] != x.shape[1:]:
-            self._acc = torch.empty((x.shape[0], 2) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
-        keep = [j for j, r in enumerate(rs.local_ids) if r < use_rows]
-        ids = [rs.local_ids[j] for j in keep]
-        e = None
-        if keep:
-            e = eps[keep[0]:keep[-1] + 1]                 # block distribution => contiguous
-        ops.blend_partial(e, masks, ids, self._acc, x.shape[0], K=K, weights=weights)
+        if self._acc is None or self._acc.shape[0] != imgs or self._acc.shape[2:] != x.shape[1:]:
+            self._acc = torch.empty((imgs, 2) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+        for i in range(imgs):
+            first, rows = rs.rows_of_image(i)
+            ids = [r for r in rows if r < use_rows]                  # contiguous block distribution => a prefix of `rows`
+            ops.blend_partial(eps[first:first + len(ids)] if ids else None, masks, ids, self._acc[i:i + 1], 1, K=K, weights=weights)
         dist.all_reduce(self._acc, group=self.pg)
-        return ops.blend_finish(x, self._acc, masks, a_t, a_next, g, is_last=is_last, out=out, K=K, weights=weights)
+        return ops.blend_finish(x, self._acc, masks, a_t, a_next, g, is_last=is_last, out=out, x0_out=x0_out, K=K, weights=weights)
 
     # ------------------------------------------------------------------ the step
     def in_fused_phase(self, t: int) -> bool:
@@ -271,6 +312,7 @@ class Tweediemix(nn.Module):
         next_t = t - self.skip
         at, at_next = self._alpha_f(t), self._alpha_f(next_t)
         self.hooks.register_time(self, t)
+        self._hook_t = t
         last = t == 1                                                     # :471-472
 
         if self.in_fused_phase(t):
@@ -297,33 +339,48 @@ class Tweediemix(nn.Module):
         else:
             rs = self._rowset("cfg", x)
             eps = self._forward(rs, x, t)
-        x_next = self._blend(x, eps, rs, 2, None, None, at, at_next, last, out)              # :421-430
-
-        if t == self.t_cond_prev and self.masks is None:                  # :431-469 (output-neutral for x_next)
-            self.masks = self._mask_handoff(x_next, next_t)
+        handoff = t == self.t_cond_prev and self.masks is None            # :431-469 (output-neutral for x_next)
+        x0 = torch.empty_like(x) if handoff else None
+        x_next = self._blend(x, eps, rs, 2, None, None, at, at_next, last, out, x0_out=x0)   # :421-430
+        if handoff:
+            self.masks = self._mask_handoff(x_next, next_t, x0)
         return x_next
 
-    def _mask_handoff(self, latent, t_start):
-        """Jump ``jumping_steps`` x 150 timesteps ahead with plain CFG (``:436-447``), decode the jumped
-        x0, write ``tweedie.jpg`` and run the segmentation subprocess (``:453-469``).  Needs a VAE and
-        the reference's ``text_segment`` stage, both outside the hot path."""
+    def decode_latent(self, latent):
+        """``fusion_sampling.py:297-303``: ``1/0.18215`` (quirk 13), VAE decode, to [0,1].  The latent is fp32 and the VAE
+        usually fp16: cast to the VAE's dtype (the reference gets the same effect from its autocast region, ``:298``)."""
+        vae_dtype = next(self.vae.parameters()).dtype if any(True for _ in self.vae.parameters()) else latent.dtype
+        img = self.vae.decode((latent / 0.18215).to(vae_dtype)).sample
+        return (img.float() / 2 + 0.5).clamp(0, 1)
+
+    def _mask_handoff(self, latent, t_start, x0):
+        """Jump ``jumping_steps`` x 150 timesteps ahead with plain CFG (``:436-447``), decode the jumped Tweedie x0 —
+        the step's own x0 when ``jumping_steps == 0`` (``:435,449-452``) — write ``tweedie.jpg`` and run the
+        segmentation subprocess (``:453-469``).  Needs a VAE and the reference's ``text_segment`` stage (or a
+        ``mask_provider`` callable), both outside the hot path."""
         if self.vae is None:
             raise RuntimeError("no precomputed masks and no VAE: cannot run the segmentation hand-off")
+        if self.group_size > 1:
+            raise RuntimeError("the segmentation hand-off is a single-process path: pass precomputed masks "
+                               "(FusionComponents.masks / --masks_dir) to a concept-parallel run")
+        if latent.shape[0] != 1:
+            raise RuntimeError("the segmentation hand-off handles one image (the reference's batch-of-one latent)")
         rs2 = self._rowset("cfg", latent)
-        lat, t_tmp, x0 = latent, t_start, latent
+        lat, t_tmp = latent, t_start
         for _ in range(max(self.config.jumping_steps, 0)):
             a_tmp = self._alpha_f(t_tmp)
             e = self._forward(rs2, lat, t_tmp)
-            t_tmp -= 150                                                  # :444 (fixed stride, quirk ⑧)
+            t_tmp -= 150                                                  # :444 (fixed stride, quirk 8)
             x0 = torch.empty_like(lat)
-            lat = ops.tweedie_blend_ddim(lat, e[:2], None, a_tmp, self._alpha_f(t_tmp), float(self.config.guidance_scale), x0_out=x0)
-        import torchvision.transforms as T
-        img = (self.vae.decode(x0 / 0.18215).sample / 2 + 0.5).clamp(0, 1)                    # :298-303
+            lat = self._blend(lat, e, rs2, 2, None, None, a_tmp, self._alpha_f(t_tmp), False, x0_out=x0)
+        img = self.decode_latent(x0)                                      # :453
         path = os.path.join(self.config.output_path, "tweedie.jpg")
-        T.ToPILImage()(img[0].float().cpu()).save(path)
+        save_image(img[0], path)                                          # :455
+        h, w = self.config.resolution_h // 8, self.config.resolution_w // 8
+        if self.mask_provider is not None:
+            return self.mask_provider(path, self.config.seg_concepts, h, w).to(self.device, torch.float32).contiguous()
         os.system(f'CUDA_VISIBLE_DEVICES={self.config.seg_gpu} python text_segment/run_expand.py --input_path={path} '
                   f'--text_condition="{self.config.seg_concepts}" --output_path={self.config.output_path}')
-        h, w = self.config.resolution_h // 8, self.config.resolution_w // 8
         return load_region_masks(self.config.output_path, self.config.seg_concepts, h, w, self.device)
 
     # ------------------------------------------------------------------ loops
@@ -352,17 +409,10 @@ class Tweediemix(nn.Module):
         """New prompts for the next image: overwrite the static text buffers in place and re-project
         the cached cross-attention K/V (captured graphs stay valid)."""
         self.text_embeds, self.text_embeds_single = text_embeds, text_embeds_single
-        E, P = text_embeds
-        for name, rs in self._rowsets.items():
-            if not rs.local_ids:
+        for (name, _), rs in self._rowsets.items():
+            if not rs.local_units:
                 continue
-            if name == "fused":
-                ehs, pool = torch.cat([E[0:1], E[2:]]), torch.cat([P[0:1], P[2:]])
-            elif name == "start":
-                Es, Ps = text_embeds_single
-                ehs, pool = torch.cat([E[0:1], E[1:2], Es[1:]]), torch.cat([P[0:1], P[1:2], Ps[1:]])
-            else:
-                ehs, pool = E[:2], P[:2]
+            ehs, pool = self._prompt_rows(name)
             rs.ehs.copy_(ehs[rs.local_ids].to(rs.ehs.device), non_blocking=True)
             rs.pooled.copy_(pool[rs.local_ids].to(rs.pooled.device), non_blocking=True)
         self.unet.refresh_text_cache()
@@ -450,9 +500,9 @@ def main(argv=None, lora: bool = False):
     latent = model.run_fusion()
     prompt_orig = opt.prompt_orig.split('+')[0] if opt.prompt_orig else 'sample'
     if model.vae is not None:
-        import torchvision.transforms as T
-        img = (model.vae.decode(latent / model.vae.config.scaling_factor).sample / 2 + 0.5).clamp(0, 1)
-        T.ToPILImage()(img[0].float().cpu()).save(os.path.join(opt.output_path, f'{prompt_orig}_{opt.seed}.png'))
+        vae_dtype = next(model.vae.parameters()).dtype                    # fp32 latent, fp16 VAE (:514-520 run under autocast)
+        img = model.vae.decode((latent / model.vae.config.scaling_factor).to(vae_dtype)).sample
+        save_image((img[0].float() / 2 + 0.5).clamp(0, 1), os.path.join(opt.output_path, f'{prompt_orig}_{opt.seed}.png'))
     else:
         torch.save(latent.cpu(), os.path.join(opt.output_path, f'{prompt_orig}_{opt.seed}.latent.pt'))
     return latent

@@ -186,6 +186,21 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
 # ------------------------------------------------------------------------------------------ k4/k5
 
 _gn_ws = {}
+_graph_pinned = False      # a CUDA graph has captured raw pointers into tmx-owned buffers
+_retired = []              # buffers superseded / evicted after that: kept alive, replays still touch them
+
+
+def pin_graph_resources() -> None:
+    """Called by the sampler after every CUDA-graph capture: from now on the GroupNorm workspace and the cached
+    cross-attention K/V tensors a graph may point at are never freed (a superseded workspace or an evicted cache entry is
+    retired into a keep-alive list instead), so a replay can never read or write recycled memory."""
+    global _graph_pinned
+    _graph_pinned = True
+
+
+def retire(obj) -> None:
+    if _graph_pinned:
+        _retired.append(obj)
 
 
 def _workspace(dev: int, nbytes: int) -> torch.Tensor:
@@ -193,6 +208,8 @@ def _workspace(dev: int, nbytes: int) -> torch.Tensor:
     if ws is None or ws.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("tmx: GroupNorm workspace would have to grow during CUDA-graph capture; run the op once eagerly first")
+        if ws is not None:
+            retire(ws)
         ws = torch.zeros(max(nbytes, 32 << 20), dtype=torch.uint8, device=f"cuda:{dev}")   # tickets must start at zero
         _gn_ws[dev] = ws
     return ws
@@ -310,6 +327,9 @@ def geglu(x, out=None):
 
 # ------------------------------------------------------------------------------------------ k3
 
+MAX_ROUTED_ROWS = 16
+
+
 def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg: int = 1, out=None):
     """Per-row routed projection (``utils_custom.py:64-82``, ``utils_lora.py:65-79,113-119``).
 
@@ -340,12 +360,16 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg: int = 
                 rank = d.shape[0] // nseg
                 assert d.dtype == x.dtype and u.dtype == x.dtype and d.is_contiguous() and u.is_contiguous()
                 assert tuple(d.shape) == (nseg * rank, Kin) and tuple(u.shape) == (Nout, rank), (d.shape, u.shape, nseg, Nout)
-    arr = lambda ts: (C.c_void_p * B)(*[None if t is None else t.data_ptr() for t in ts]) if ts is not None else None
-    wp, dp, up = arr(weights), arr(lora_down), arr(lora_up)
     launches = (1 if weights is not None else 0) + (1 if rank else 0)
-    with _Launch("routed_linear", launches, f"M{M}_K{Kin}_N{Nout}", 2.0 * B * M * Kin * Nout if weights is not None else 0.0):
-        rc = _lib.load().tmx_routed_linear_fwd(_p(x), wp, dp, up, _p(out), B, M, Kin, Nout, int(rank), int(nseg), _dt(x), _stream())
-    _lib.check(rc, "tmx_routed_linear_fwd")
+    for b0 in range(0, B, MAX_ROUTED_ROWS):                    # the ABI takes at most 16 batch rows per call
+        nb = min(MAX_ROUTED_ROWS, B - b0)
+        arr = lambda ts: (C.c_void_p * nb)(*[None if t is None else t.data_ptr() for t in ts[b0:b0 + nb]]) if ts is not None else None
+        wp, dp, up = arr(weights), arr(lora_down), arr(lora_up)
+        if weights is None and all(t is None for t in lora_down[b0:b0 + nb]):
+            continue
+        with _Launch("routed_linear", launches, f"M{M}_K{Kin}_N{Nout}", 2.0 * nb * M * Kin * Nout if weights is not None else 0.0):
+            rc = _lib.load().tmx_routed_linear_fwd(_p(x[b0:]), wp, dp, up, _p(out[b0:]), nb, M, Kin, Nout, int(rank), int(nseg), _dt(x), _stream())
+        _lib.check(rc, "tmx_routed_linear_fwd")
     return out
 
 

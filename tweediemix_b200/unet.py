@@ -191,7 +191,7 @@ class TmxAttention(nn.Module):
         hit = self._kv_cache.get(key)
         if hit is None:
             if len(self._kv_cache) >= 16:                   # callers that stream fresh tensors: drop the oldest
-                self._kv_cache.pop(next(iter(self._kv_cache)))
+                ops.retire(self._kv_cache.pop(next(iter(self._kv_cache))))   # (kept alive if a CUDA graph may point at it)
             kv = self._project_kv(ehs, routing)
             self._kv_cache[key] = (ehs, routing, kv)
             return kv
