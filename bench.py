@@ -20,8 +20,12 @@ Weights, text embeddings and the start latent are seeded synthetic data (no netw
                  events in an instrumented eager pass of one fused denoise step, after the timed region.
   cpu_baseline : oracle port of the reference's PyTorch CPU path on the host cores (rank 0, N=1).
 
-Multi-GPU (--gpus N): concept-parallel groups of G = min(N, K+1 = 4) ranks share one image (batch
-rows sharded, one all-reduce per step); N/G groups run different images concurrently.
+Multi-GPU (--gpus N): concept-parallel groups of G ranks share one image batch ((image, prompt row) units
+sharded, one all-reduce per step); N/G groups sample different images concurrently.  G defaults to the size
+that maximises images/s for the config (configs[1]: 2; --group-size overrides).  `--config 2|3` runs the
+LoRA / K=8 x batch-4 BASELINE configs as the main line; on the default run they ride along as extra legs
+under `other_configs` when enough GPUs are present (configs[2] at >= 4, configs[3] at 8).  Before timing,
+a multi-rank run checks its sharded latents against the same model run unsharded (`concept_parallel_check`).
 """
 from __future__ import annotations
 
@@ -38,10 +42,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-K_CONCEPTS = 3                      # concept_num incl. background (BASELINE "K=2 (cat+dog)" + background)
-FORWARDS_PER_IMAGE = 242
+K_CONCEPTS = 3                      # configs[1]: concept_num incl. background (BASELINE "K=2 (cat+dog)" + background)
+FORWARDS_PER_IMAGE = 242            # configs[1]; other configs report the count the sampler actually executed
 MASK_DIR = os.path.join(ROOT, "tests", "golden", "masks", "test_out")
 MASK_NAMES = "a cat+a dog"
+
+# BASELINE.json configs this file can run ("K" there counts foreground concepts; concept_num adds the background).
+CONFIGS = {
+    1: dict(name="configs[1]", variant="custom", concept_num=3, image_batch=1, group=None,
+            text="SDXL-base U-Net 1024x1024 (latent 128x128), K=2 concepts + background (concept_num 3, U-Net batch 4), "
+                 "50 DDIM steps, guidance 0.8, t_cond 0.2, 10 resampling iterations; masks precomputed"),
+    2: dict(name="configs[2]", variant="lora", concept_num=3, image_batch=1, group=4,
+            text="SDXL-base U-Net 1024x1024, K=3 LoRA concept rows + unconditional row (fusion_sampling_lora.py, t_stop 0.8), "
+                 "50 DDIM steps, rank-4 LoRA on q/k/v/out of all 140 attentions; batch rows sharded over up to 4 GPUs"),
+    3: dict(name="configs[3]", variant="custom", concept_num=9, image_batch=4, group=8,
+            text="SDXL-base U-Net 1024x1024, K=8 concepts + background (concept_num 9, 10 prompt rows) x image batch 4 = 40 "
+                 "(image, row) units per step, 50 DDIM steps; units sharded over up to 8 GPUs (5 per rank at N=8)"),
+}
 
 
 def parse():
@@ -50,17 +67,51 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--variant", default="custom", choices=["custom", "lora"])
+    p.add_argument("--config", type=int, default=1, choices=[1, 2, 3], help="BASELINE.json configs[i] to run as the main line")
+    p.add_argument("--variant", default=None, choices=["custom", "lora"], help="override the config's hook variant")
+    p.add_argument("--concepts", type=int, default=None, help="override concept_num (incl. background); U-Net rows = concepts + 1")
+    p.add_argument("--image-batch", type=int, default=None, help="images sampled together by one concept-parallel group")
+    p.add_argument("--group-size", type=int, default=None,
+                   help="ranks per concept-parallel group (default: configs[1] -> 2, the size that maximises images/s; "
+                        "configs[2] -> 4, configs[3] -> 8; always clamped to the GPU and unit count)")
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     p.add_argument("--workload", default="image50", choices=["image50", "fused_step"],
-                   help="image50 = one full 50-step image per step (the metric); fused_step = one fused-phase denoise step (profiling)")
+                   help="image50 = one full 50-step image (batch) per step (the metric); fused_step = one fused-phase denoise step (profiling)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graphs", action="store_true")
+    p.add_argument("--no-extra-configs", action="store_true",
+                   help="skip the extra legs (configs[2] at >= 4 GPUs, configs[3] at 8 GPUs) reported under other_configs")
+    p.add_argument("--no-rank-check", action="store_true", help="skip the N-rank vs 1-rank latent check before timing")
     p.add_argument("--seed", type=int, default=3821)
     p.add_argument("--ncu-range", action="store_true",
                    help="profiling aid: after warm-up run ONE eager fused denoise step between cudaProfilerStart/Stop and exit "
                         "(use with ncu --profile-from-start off)")
     return p.parse_args()
+
+
+def resolve_spec(args, world, config=None):
+    """The workload of one leg: BASELINE config + command-line overrides + the group-size policy."""
+    c = dict(CONFIGS[config if config is not None else args.config])
+    if config is None:
+        if args.variant:
+            c["variant"] = args.variant
+        if args.concepts:
+            c["concept_num"] = args.concepts
+        if args.image_batch:
+            c["image_batch"] = args.image_batch
+        if args.group_size:
+            c["group"] = args.group_size
+    units = (c["concept_num"] + 1) * c["image_batch"]
+    if c["group"] is None:
+        # configs[1]: 4 units per image.  Measured (profiles/README.md): a 2-rank group keeps 0.87 of the per-GPU rate
+        # (18.9 vs 33.5/2 ms per fused step, both 2-row phases split evenly), a 4-rank group 0.61 (a one-row forward is
+        # 12.0 ms, and the 2-row phases leave two ranks idle) -> images/s is maximised by 2-rank groups.
+        c["group"] = 2
+    c["group"] = max(1, min(c["group"], world, units))
+    while world % c["group"]:
+        c["group"] -= 1
+    c["n_groups"] = world // c["group"]
+    return c
 
 
 def namespace(variant):
@@ -135,16 +186,17 @@ def run_reference(args):
     if rank != 0:
         return 0
     from oracle.cpu_baseline import CpuReference
+    spec = resolve_spec(args, max(args.gpus, 1))
     ref = CpuReference(res=1024)
     for _ in range(min(args.warmup, 1)):            # one warm-up forward is enough on CPU (allocator, thread pool)
         ref.forward_seconds()
     t = [ref.forward_seconds() for _ in range(args.steps)]
     sec = sum(t) / len(t)
-    val = CpuReference.images_per_second(sec)
+    val = 1.0 / (forwards_per_image(spec) * sec)
     line = {"impl": "reference", "metric": "1024px images/sec @50 DDIM steps, K concepts", "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / val,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, min(max(args.gpus, 1), K_CONCEPTS + 1), max(max(args.gpus, 1) // min(max(args.gpus, 1), K_CONCEPTS + 1), 1)),
+            "higher_is_better": True, "scaling": scaling_label(spec), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, spec),
             "gpu_launches": 0,
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": ref.threads, "kind": "port", "sample": ref.sample_description(),
                              "seconds_per_sample_forward": sec},
@@ -153,16 +205,172 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args, group, n_groups):
-    return {"workload": "SDXL-base U-Net 1024x1024 (latent 128x128), K=2 concepts + background (concept_num 3, U-Net batch 4), "
-                        "50 DDIM steps, guidance 0.8, t_cond 0.2, 10 resampling iterations; masks precomputed",
-            "baseline_config": "configs[1]", "variant": args.variant, "step_unit": "one 50-step image" if args.workload == "image50" else "one fused denoise step",
-            "sample_forwards_per_image": FORWARDS_PER_IMAGE, "parallelism": f"concept-parallel x{group}, {n_groups} image group(s)",
+def forwards_per_image(spec, n=50, t_cond=0.2, t_stop=0.8, resampling=10):
+    """U-Net sample-forwards that shape one image (the output-neutral jump is not run, masks are inputs):
+    start step (K+1)(1+R) + 2R, plain-CFG steps 2 each, fused steps K+1 each."""
+    rows = spec["concept_num"] + 1
+    ic = int(n * t_cond)
+    fused = (int(n * t_stop) - ic + 1) if spec["variant"] == "lora" else (n - ic)
+    return rows * (1 + resampling) + 2 * resampling + 2 * (n - 1 - fused) + rows * fused
+
+
+def scaling_label(spec):
+    """'strong' while ONE concept-parallel group shares the job (total work fixed, split over more GPUs); 'weak' once
+    further GPUs add further groups that sample their own images (per-GPU work fixed)."""
+    return "weak" if spec["n_groups"] > 1 else "strong"
+
+
+def workload_config(args, spec):
+    g, ng, ib = spec["group"], spec["n_groups"], spec["image_batch"]
+    return {"workload": spec["text"],
+            "baseline_config": spec["name"], "variant": spec["variant"], "concept_num": spec["concept_num"], "image_batch": ib,
+            "step_unit": (f"one 50-step image batch ({ib} image(s)) per group" if args.workload == "image50" else "one fused denoise step"),
+            "sample_forwards_per_image": forwards_per_image(spec),
+            "parallelism": f"concept-parallel x{g} (batch rows sharded, one all-reduce per step), {ng} image group(s)",
+            "group_size": g, "image_groups": ng,
             "cuda_graphs": not args.no_graphs,
             "l2": "no flush needed: every step streams 5.1 GB of bf16 weights (>> 126 MB L2)"}
 
 
 # ================================================================================ our arm (GPU)
+
+class Leg:
+    """One workload (a BASELINE config) set up on this process' GPU: model, host buffers, step functions."""
+
+    def __init__(self, args, spec, world, rank, dev, torch, dist):
+        from tweediemix_b200.fusion_sampling import Tweediemix, make_concept_groups
+        from tweediemix_b200.masks import load_region_masks, stripe_masks
+        from tweediemix_b200.synthetic import make_components, make_text
+        from tweediemix_b200.unet import UNetConfig
+        self.args, self.spec, self.world, self.rank, self.dev, self.torch, self.dist = args, spec, world, rank, dev, torch, dist
+        K, ib = spec["concept_num"], spec["image_batch"]
+        gs, n_groups, my_group, pg = make_concept_groups(world, rank, (K + 1) * ib, spec["group"])
+        assert gs == spec["group"] and n_groups == spec["n_groups"], (gs, n_groups, spec)
+        self.group_size, self.n_groups, self.my_group, self.pg = gs, n_groups, my_group, pg
+        dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+        if K == 3:
+            masks = load_region_masks(MASK_DIR, MASK_NAMES, 128, 128)        # the reference's shipped cat / dog masks
+        else:
+            masks = stripe_masks(K, 128, 128)                               # no fixture for other K: stripe partition
+        self.masks_host = masks.pin_memory()
+        comp = make_components(K, spec["variant"], seed=args.seed, device=dev, dtype=dtype, masks=self.masks_host)
+        self.comp = comp
+        self.model = model = Tweediemix(namespace(spec["variant"]), comp, variant=spec["variant"],
+                                        use_cuda_graphs=not args.no_graphs, process_group=pg if gs > 1 else None)
+        ns = model.config
+        if spec["variant"] == "lora":
+            model.init_fusion(int(ns.n_timesteps * ns.t_cond), int(ns.n_timesteps * ns.t_stop))
+        else:
+            model.init_fusion(int(ns.n_timesteps * ns.t_cond))
+        gen = torch.Generator().manual_seed(args.seed + 17 * my_group)
+        self.x_host = torch.randn(ib, 4, 128, 128, generator=gen).pin_memory()   # CPU-generator draw, like fusion_sampling.py:488
+        text_host, single_host = make_text(UNetConfig.sdxl_base(), K, args.seed + 1, dtype=dtype)
+        self.text_host = tuple(t.pin_memory() for t in text_host)
+        self.single_host = tuple(t.pin_memory() for t in single_host)
+        self.out_host = torch.empty(ib, 4, 128, 128).pin_memory()
+        self.x_dev = self.x_host.to(dev)
+        self.fused_t = [t for t in model._timesteps if model.in_fused_phase(t)]
+        self.h2d = self.masks_host.numel() * 4 + self.x_host.numel() * 4 + sum(t.numel() * t.element_size() for t in self.text_host + self.single_host)
+        self.d2h = self.out_host.numel() * 4
+
+    def step_resident(self):
+        if self.args.workload == "image50":
+            return self.model.sample_loop(self.x_dev)
+        return self.model.denoise_step(self.x_dev, self.fused_t[0])
+
+    def step_e2e(self):
+        torch, dev, m = self.torch, self.dev, self.model
+        m.set_masks(self.masks_host.to(dev, non_blocking=True))
+        m.set_text(tuple(t.to(dev, non_blocking=True) for t in self.text_host), tuple(t.to(dev, non_blocking=True) for t in self.single_host))
+        x = self.x_host.to(dev, non_blocking=True)
+        y = m.sample_loop(x) if self.args.workload == "image50" else m.denoise_step(x, self.fused_t[0])
+        self.out_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def sync_all(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        torch = self.torch
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def rank_check(self, n_steps=13):
+        """Concept-parallel sanity check before timing: the first `n_steps` denoise steps (start step with its resampling
+        loop, the plain-CFG steps, the first fused steps) through the sharded path (partial -> NCCL all-reduce -> finish)
+        against the SAME model run unsharded on this rank.  The two differ by 16-bit rounding only (cuBLAS / cuDNN pick
+        other kernels for a 1- or 2-row batch than for 4 rows), so the bound is relative: 5e-2 of max|x|; the latents of
+        the ranks of a group must be bit-identical."""
+        torch, dist, m = self.torch, self.dist, self.model
+        if self.group_size == 1:
+            return None
+        ts = m._timesteps[:n_steps]
+        x = self.x_dev.clone()
+        for t in ts:
+            x = m.denoise_step(x, t)
+        gathered = [torch.empty_like(x) for _ in range(self.group_size)]
+        dist.all_gather(gathered, x, group=self.pg)
+        identical = all(torch.equal(gathered[0], g) for g in gathered[1:])
+        pg, gs, gr, graphs, rowsets = m.pg, m.group_size, m.group_rank, m.use_cuda_graphs, m._rowsets
+        m.pg, m.group_size, m.group_rank, m.use_cuda_graphs, m._rowsets = None, 1, 0, False, {}
+        try:
+            y = self.x_dev.clone()
+            for t in ts:
+                y = m.denoise_step(y, t)
+        finally:
+            m.pg, m.group_size, m.group_rank, m.use_cuda_graphs, m._rowsets = pg, gs, gr, graphs, rowsets
+        diff = float((x - y).abs().max().item())
+        scale = float(y.abs().max().item())
+        res = {"steps": len(ts), "max_abs_diff": diff, "max_abs_latent": scale, "rel": diff / scale, "ranks_bit_identical": identical}
+        if not identical or not (diff <= 5e-2 * scale):
+            raise RuntimeError(f"concept-parallel check failed on rank {self.rank}: {res}")
+        return res
+
+    def measure(self, steps, warmup):
+        """Warm-up, timed resident + e2e regions, per-denoise-step ms.  Returns a dict (identical on every rank)."""
+        from tweediemix_b200 import ops
+        torch = self.torch
+        m = self.model
+        check = None if self.args.no_rank_check else self.rank_check()
+        m.n_forward_rows = 0
+        for _ in range(warmup):
+            self.step_resident()
+        rows = torch.tensor([float(m.n_forward_rows)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(rows)
+        launches0 = ops.launch_count()
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        with ClockSampler(local) as clk:
+            total_ms = self.timed(self.step_resident, steps)
+        launches = ops.launch_count() - launches0
+        clocks = clk.summary()
+        self.step_e2e()                                      # warm (first set_text re-projects K/V)
+        e2e_ms = self.timed(self.step_e2e, steps)
+        images_per_step = self.n_groups * self.spec["image_batch"]      # images finished per benchmark step, whole job
+        ms_per_step = total_ms / steps
+        n_f = 8
+        m.denoise_step(self.x_dev, self.fused_t[0])
+        fused_ms = self.timed(lambda: m.denoise_step(self.x_dev, self.fused_t[1]), n_f) / n_f
+        unit = "images/s" if self.args.workload == "image50" else "steps/s"
+        return {"value": images_per_step * 1000.0 / ms_per_step, "unit": unit, "ms_per_step": ms_per_step,
+                "e2e": {"value": images_per_step * 1000.0 / (e2e_ms / steps), "unit": unit,
+                        "h2d_bytes_per_step": self.h2d * self.world, "d2h_bytes_per_step": self.d2h * self.world,   # every rank copies its replica
+                        "ms_per_step": e2e_ms / steps},
+                "per_denoise_step_ms": fused_ms, "clocks": clocks, "gpu_launches": launches,
+                "sample_forwards_executed_per_image": (rows.item() / max(warmup, 1)) / images_per_step if warmup and self.args.workload == "image50" else None,
+                "concept_parallel_check": check}
+
 
 def run_ours(args):
     import torch
@@ -182,66 +390,11 @@ def run_ours(args):
         build.build()
     if world > 1:
         dist.barrier()
-    from tweediemix_b200.fusion_sampling import Tweediemix
-    from tweediemix_b200.masks import load_region_masks
-    from tweediemix_b200.synthetic import make_components, make_text
-    from tweediemix_b200.unet import UNetConfig
 
-    from tweediemix_b200.fusion_sampling import make_concept_groups
-    group_size, n_groups, my_group, pg = make_concept_groups(world, rank, K_CONCEPTS + 1)
+    spec = resolve_spec(args, world)
+    leg = Leg(args, spec, world, rank, dev, torch, dist)
+    model, x_dev, fused_t = leg.model, leg.x_dev, leg.fused_t
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    masks_host = load_region_masks(MASK_DIR, MASK_NAMES, 128, 128).pin_memory()
-    comp = make_components(K_CONCEPTS, args.variant, seed=args.seed, device=dev, dtype=dtype, masks=masks_host)
-    model = Tweediemix(namespace(args.variant), comp, variant=args.variant, use_cuda_graphs=not args.no_graphs,
-                       process_group=pg if group_size > 1 else None)
-    ns = model.config
-    if args.variant == "lora":
-        model.init_fusion(int(ns.n_timesteps * ns.t_cond), int(ns.n_timesteps * ns.t_stop))
-    else:
-        model.init_fusion(int(ns.n_timesteps * ns.t_cond))
-
-    gen = torch.Generator().manual_seed(args.seed + 17 * my_group)
-    x_host = torch.randn(1, 4, 128, 128, generator=gen).pin_memory()          # CPU-generator draw, like fusion_sampling.py:488
-    text_host, single_host = make_text(UNetConfig.sdxl_base(), K_CONCEPTS, args.seed + 1, dtype=dtype)
-    text_host = tuple(t.pin_memory() for t in text_host)
-    single_host = tuple(t.pin_memory() for t in single_host)
-    out_host = torch.empty(1, 4, 128, 128).pin_memory()
-    x_dev = x_host.to(dev)
-    fused_t = [t for t in model._timesteps if model.in_fused_phase(t)]
-
-    def step_resident():
-        if args.workload == "image50":
-            return model.sample_loop(x_dev)
-        return model.denoise_step(x_dev, fused_t[0])
-
-    def step_e2e():
-        model.set_masks(masks_host.to(dev, non_blocking=True))
-        model.set_text(tuple(t.to(dev, non_blocking=True) for t in text_host), tuple(t.to(dev, non_blocking=True) for t in single_host))
-        x = x_host.to(dev, non_blocking=True)
-        y = model.sample_loop(x) if args.workload == "image50" else model.denoise_step(x, fused_t[0])
-        out_host.copy_(y, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    h2d = masks_host.numel() * 4 + x_host.numel() * 4 + sum(t.numel() * t.element_size() for t in text_host + single_host)
-    d2h = out_host.numel() * 4
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
 
     if args.ncu_range:
         model.use_cuda_graphs = False
@@ -254,25 +407,7 @@ def run_ours(args):
         torch.cuda.profiler.stop()
         return 0
 
-    for _ in range(args.warmup):
-        step_resident()
-    launches0 = ops.launch_count()
-    with ClockSampler(local) as clk:
-        total_ms = timed(step_resident, args.steps)
-    launches = ops.launch_count() - launches0
-    clocks = clk.summary()
-    step_e2e()                                           # warm (first set_text re-projects K/V)
-    e2e_ms = timed(step_e2e, args.steps)
-
-    units_per_step = n_groups                            # images (or fused steps) finished per benchmark step, whole job
-    ms_per_step = total_ms / args.steps
-    value = units_per_step * 1000.0 / ms_per_step
-    e2e_value = units_per_step * 1000.0 / (e2e_ms / args.steps)
-
-    # per-denoise-step ms of the fused phase (second half of the BASELINE metric)
-    n_f = 8
-    model.denoise_step(x_dev, fused_t[0])
-    fused_ms = timed(lambda: model.denoise_step(x_dev, fused_t[1]), n_f) / n_f
+    main = leg.measure(args.steps, args.warmup)
 
     # ---- roofline of the hand-written kernels: instrumented EAGER fused step, CUDA events per launch
     roof, others = None, []
@@ -308,13 +443,26 @@ def run_ours(args):
                 gbs = work / (ms * 1e-3) / 1e9
                 others.append({"kernel": f, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                                "calls": n, "total_ms": ms})
+    for f in ("linear",):
+        if f in fam:
+            work = sum(d["work"] for _, d in fam[f]); ms = sum(d["ms"] for _, d in fam[f]); n = sum(d["launches"] for _, d in fam[f])
+            if ms > 0:
+                tfs = work / (ms * 1e-3) / 1e12
+                others.append({"kernel": "linear_kernel (tcgen05 GEMM + fused epilogues, all launches of one fused step)", "bound": "tensor",
+                               "achieved": tfs, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": tfs / pk["tensor_sustained"],
+                               "calls": n, "total_ms": ms,
+                               "by_shape": {tag: {"launches": d["launches"], "avg_ms": d["ms"] / d["launches"],
+                                                  "tflops": d["work"] / (d["ms"] * 1e-3) / 1e12} for tag, d in fam[f]}})
     step_kernel_ms = {f: sum(d["ms"] for _, d in v) for f, v in fam.items()}
+    eager_note = ("per-launch CUDA events in an eager step; with one or two batch rows per GPU the launches are host-bound and these "
+                  "per-kernel times over-state the device time" if spec["group"] > 1 else "per-launch CUDA events in an eager step")
 
     # k7 at a size where HBM (not launch latency) is the bound: 2048 stacked images (2.5 GB)
     try:
         imgs = 2048
+        Kc = spec["concept_num"]
         xb = torch.randn(imgs, 4, 128, 128, device=dev)
-        eb = torch.randn(imgs, K_CONCEPTS + 1, 4, 128, 128, device=dev, dtype=dtype)
+        eb = torch.randn(imgs, Kc + 1, 4, 128, 128, device=dev, dtype=dtype)
         mb = model.masks
         ob = torch.empty_like(xb)
         for _ in range(3):
@@ -326,13 +474,34 @@ def run_ours(args):
             ops.tweedie_blend_ddim(xb, eb, mb, 0.0438, 0.0518, 0.8, out=ob)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        nbytes = imgs * (4 * 16384 * 8 + 4 * 4 * 16384 * eb.element_size()) + K_CONCEPTS * 16384 * 4
+        nbytes = imgs * (4 * 16384 * 8 + (Kc + 1) * 4 * 16384 * eb.element_size()) + Kc * 16384 * 4
         gbs = nbytes / (ms * 1e-3) / 1e9
         others.append({"kernel": "blend (k7) on 2048 stacked images", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                        "frac": gbs / pk["hbm"], "avg_launch_ms": ms, "bytes_per_launch": nbytes})
         del xb, eb, ob
     except Exception as e:                                 # never let the side measurement break the headline
         others.append({"kernel": "blend (k7) on 2048 stacked images", "error": str(e)})
+
+    # ---- extra legs: the BASELINE configs that need several GPUs ride on the driver's 4- and 8-GPU runs
+    extra = []
+    if not args.no_extra_configs and args.config == 1 and args.workload == "image50":
+        for cfg_id, need in ((2, 4), (3, 8)):
+            if world < need:
+                continue
+            entry = {"baseline_config": CONFIGS[cfg_id]["name"]}
+            try:
+                torch.cuda.empty_cache()
+                sp = resolve_spec(args, world, cfg_id)
+                lg = Leg(args, sp, world, rank, dev, torch, dist)
+                r = lg.measure(max(1, min(args.steps, 2)), 1)
+                entry.update({"config": workload_config(args, sp), "scaling": scaling_label(sp), "n_gpus": world, **r})
+                del lg
+            except Exception as e:                         # an extra leg must never take the headline line down with it
+                entry["error"] = f"{type(e).__name__}: {e}"
+                if world > 1:                              # the ranks may have diverged: do not attempt further collectives
+                    extra.append(entry)
+                    break
+            extra.append(entry)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -341,22 +510,25 @@ def run_ours(args):
             torch.cuda.empty_cache()
             ref = CpuReference(res=1024)
             sec = ref.forward_seconds()
-            cpu = {"value": CpuReference.images_per_second(sec), "unit": "images/s", "cores": ref.threads, "kind": "port",
+            cpu = {"value": 1.0 / (forwards_per_image(spec) * sec), "unit": "images/s", "cores": ref.threads, "kind": "port",
                    "sample": ref.sample_description(), "seconds_per_sample_forward": sec}
         except Exception as e:
             cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
     if rank == 0:
         metric = "1024px images/sec @50 DDIM steps, K concepts" if args.workload == "image50" else "fused denoise steps/sec (profiling workload)"
-        line = {"metric": metric, "value": value, "unit": "images/s" if args.workload == "image50" else "steps/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": workload_config(args, group_size, n_groups),
-                "per_denoise_step_ms": fused_ms, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "images/s" if args.workload == "image50" else "steps/s",
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "gpu_launches_by_kernel": {k: v for k, v in ops.LAUNCHES.items()},
+        line = {"metric": metric, "value": main["value"], "unit": main["unit"],
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+                "higher_is_better": True, "scaling": scaling_label(spec), "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": workload_config(args, spec),
+                "per_denoise_step_ms": main["per_denoise_step_ms"], "clocks": main["clocks"],
+                "e2e": main["e2e"],
+                "gpu_launches": main["gpu_launches"], "gpu_launches_by_kernel": {k: v for k, v in ops.LAUNCHES.items()},
+                "sample_forwards_executed_per_image": main["sample_forwards_executed_per_image"],
+                "concept_parallel_check": main["concept_parallel_check"],
                 "roofline": roof, "roofline_other": others, "fused_step_tmx_kernel_ms": step_kernel_ms,
+                "fused_step_tmx_kernel_ms_note": eager_note,
+                "other_configs": extra,
                 "cpu_baseline": cpu}
         _emit(line)
     if world > 1:

@@ -109,12 +109,12 @@ def _patch(mod, fn, gate):
 
 def register_custom_ref(unet, concept_unets, t_cond, num_concepts: int, gate: int = REFERENCE_GATE):
     """utils_custom.py:113-157.  ``concept_unets[i]`` plays ``model.unet_{i}``."""
-    donors = [dict(transformer_blocks_in_hook_order(u)) for u in concept_unets]
     for name, blk in transformer_blocks_in_hook_order(unet):
         m = blk.attn2
         for i in range(num_concepts):
-            setattr(m, f"to_k_{i}", donors[i][name].attn2.to_k)
-            setattr(m, f"to_v_{i}", donors[i][name].attn2.to_v)
+            donor = concept_unets[i].get_submodule(name + ".attn2")     # a full U-Net or any tree with these leaves
+            setattr(m, f"to_k_{i}", donor.to_k)
+            setattr(m, f"to_v_{i}", donor.to_v)
         m.t_cond, m.num_concepts = t_cond, num_concepts
         _patch(m, custom_forward_ref, gate)
 

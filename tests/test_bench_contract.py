@@ -38,7 +38,8 @@ def test_reference_arm_line(monkeypatch, capsys):
     assert abs(line["value"] - 1.0 / (2.0 * 242)) < 1e-12                      # 242 sample-forwards per 50-step image
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 3
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["config"]["baseline_config"] == "configs[1]" and line["config"]["parallelism"] == "concept-parallel x4, 1 image group(s)"
+    assert line["config"]["baseline_config"] == "configs[1]" and line["config"]["group_size"] == 2 and line["config"]["image_groups"] == 2
+    assert line["scaling"] == "weak" and line["config"]["sample_forwards_per_image"] == 242
     # other ranks of a torchrun launch print nothing and exit 0
     monkeypatch.setenv("RANK", "1")
     assert b.run_reference(args) == 0 and capsys.readouterr().out == ""
@@ -61,3 +62,21 @@ def test_stdout_carries_only_the_json_line():
     assert r.returncode == 0, r.stderr
     assert r.stdout == '{"ok": 1}\n'
     assert "NCCL version banner" in r.stderr and "python chatter" in r.stderr
+
+
+def test_workload_specs(monkeypatch):
+    """Group-size policy and the forward counts of the three runnable BASELINE configs."""
+    b = _load_bench()
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    args = b.parse()
+    for world, want in ((1, (1, 1)), (2, (2, 1)), (4, (2, 2)), (8, (2, 4))):
+        sp = b.resolve_spec(args, world)
+        assert (sp["group"], sp["n_groups"]) == want and b.scaling_label(sp) == ("weak" if want[1] > 1 else "strong")
+    sp2 = b.resolve_spec(args, 4, 2)
+    assert (sp2["variant"], sp2["group"], sp2["n_groups"]) == ("lora", 4, 1) and b.forwards_per_image(sp2) == 224
+    sp3 = b.resolve_spec(args, 8, 3)
+    assert (sp3["concept_num"], sp3["image_batch"], sp3["group"], sp3["n_groups"]) == (9, 4, 8, 1)
+    assert b.forwards_per_image(b.resolve_spec(args, 1)) == 242
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--group-size", "4", "--gpus", "8"])
+    sp = b.resolve_spec(b.parse(), 8)
+    assert (sp["group"], sp["n_groups"]) == (4, 2)

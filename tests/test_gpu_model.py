@@ -69,10 +69,10 @@ def test_unet_forward_vs_oracle(dtype):
     assert _rel(got, want) <= TOL_FWD[dtype]
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("variant", ["custom", "lora"])
 @pytest.mark.parametrize("t,batch", [(781, 4), (981, 4), (761, 2)])
-def test_hooked_forward_vs_oracle(variant, t, batch):
-    dtype = torch.float16
+def test_hooked_forward_vs_oracle(variant, t, batch, dtype):
     ref = synth.make_base_unet(T.RCFG, 1)
     lora = variant == "lora"
     extra = [make_lora_set(ref, 20 + i, up_std=0.05) for i in range(K)] if lora else \

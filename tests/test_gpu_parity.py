@@ -1,0 +1,204 @@
+"""-m gpu: the parity evidence VERDICT r01 asked for.
+
+(1) Side by side, on the same seeded 10-step runs (custom and LoRA, narrow SDXL-topology U-Net, 256x256):
+        |ref_fp16  - oracle_fp32|   the REFERENCE's execution mode — oracle/unet_ref.py + oracle/hooks_ref.py (pinned against
+                                    the reference's own hook files) with fp16 weights on CUDA under torch.autocast(fp16),
+                                    exactly how fusion_sampling.py:492 runs
+        |prod_fp16 - oracle_fp32|   the product, fp16
+        |prod_bf16 - oracle_fp32|   the product, bf16 (the benchmarked dtype)
+        |prod_fp16 - ref_fp16|
+    relative to max|oracle latent|.  Bound: the product may deviate from the fp32 oracle at most 2x as far as the
+    reference's own fp16 execution does (bf16: x8 on top, its mantissa is 3 bits shorter), floor 5e-3.
+(2) Full-width SDXL-base config (C = 320/640/1280, cross dim 2048): product vs fp32 oracle with the SAME (16-bit rounded)
+    weights — batch 4 at latent 32x32 routed custom + LoRA in fp16 and bf16, and two rows at latent 128x128 (both
+    GroupNorm paths, 4096-token attention).  Bound: 1.5e-2 (fp16) / 6e-2 (bf16) of max|oracle eps|.
+(3) K = 8 concepts through the whole sampler (gate K+1 instead of the literal 4, utils_custom.py:61-62).
+(4) An image batch of 2 equals two single-image runs.
+"""
+import copy
+import types
+
+import pytest
+import torch
+
+import test_host_logic as T
+from oracle import synth
+from oracle.hooks_ref import make_lora_set, register_custom_ref, register_lora_ref, register_time_ref
+from oracle.sampler_ref import RefConfig, TweediemixRef
+
+pytestmark = pytest.mark.gpu
+K = 3
+
+
+def _build():
+    from tweediemix_b200 import build
+    build.build()
+
+
+def _extras(ref_unet, k, lora):
+    return [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(k)] if lora else \
+           [synth.make_concept_unet(ref_unet, 10 + i) for i in range(k)]
+
+
+def _gpu_product(ref_unet, extra, lora, n, res, dtype, k=K, graphs=True):
+    from tweediemix_b200.fusion_sampling import FusionComponents, Tweediemix
+    s = T._product_sampler(ref_unet, extra, lora, n, res, k=k)
+    comp = FusionComponents(unet=s.unet.to("cuda", dtype).finalize(),
+                            concept_unets=[getattr(s, f"unet_{i}") for i in range(k)],
+                            text_embeds=s.text_embeds, text_embeds_single=s.text_embeds_single, masks=s.masks)
+    m = Tweediemix(T._namespace(n, res, lora), comp, variant="lora" if lora else "custom", use_cuda_graphs=graphs)
+    m.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else m.init_fusion(int(n * 0.2))
+    return m
+
+
+def _reference_mode_sampler(ref_unet, extra, lora, n, res, k=K):
+    """The oracle sampler + oracle hooks moved to CUDA with fp16 weights; the caller runs it under autocast(fp16)."""
+    unet = copy.deepcopy(ref_unet).to("cuda", torch.float16)
+    if lora:
+        ex = [{name: {kk: copy.deepcopy(v).to("cuda", torch.float16) for kk, v in layers.items()} for name, layers in ls.items()} for ls in extra]
+    else:
+        ex = [copy.deepcopy(u).to("cuda", torch.float16) for u in extra]
+    text, single = synth.make_text(T.RCFG, k, 77)
+    cu = lambda tup: tuple(t.to("cuda", torch.float16) for t in tup)
+    cfg = RefConfig(n_timesteps=n, resolution_h=res, resolution_w=res, t_stop=0.8 if lora else None, resampling_steps=2)
+    s = TweediemixRef(unet, cu(text), cu(single), T._masks_for(k, res // 8, res // 8).cuda(), cfg, k, lora=lora, run_jump=False)
+    (register_lora_ref if lora else register_custom_ref)(unet, ex, s.hook_gate_window(), k, gate=k + 1)
+    return s
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_deviation_side_by_side_with_reference_fp16_mode(lora):
+    _build()
+    n, res = 10, 256
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = _extras(ref_unet, K, lora)
+    orc = T._oracle_sampler(ref_unet, extra, lora, n, res)
+    x0 = orc.initial_latent()
+    o32 = orc.sample_loop(x0.clone())
+    ref = _reference_mode_sampler(synth.make_base_unet(T.RCFG, 1), _extras(synth.make_base_unet(T.RCFG, 1), K, lora), lora, n, res)
+    with torch.autocast("cuda", dtype=torch.float16):
+        r16 = ref.sample_loop(x0.clone().cuda()).float().cpu()
+    assert ref.n_forward_rows == orc.n_forward_rows
+    p16 = _gpu_product(ref_unet, extra, lora, n, res, torch.float16).sample_loop(x0.clone()).cpu()
+    pbf = _gpu_product(ref_unet, extra, lora, n, res, torch.bfloat16).sample_loop(x0.clone()).cpu()
+    scale = o32.abs().max().item()
+    d = lambda a, b: (a - b).abs().max().item() / scale
+    row = {"ref_fp16_vs_oracle_fp32": d(r16, o32), "prod_fp16_vs_oracle_fp32": d(p16, o32),
+           "prod_bf16_vs_oracle_fp32": d(pbf, o32), "prod_fp16_vs_ref_fp16": d(p16, r16)}
+    print(f"PARITY side-by-side lora={lora} (10 steps, 256x256, rel. to max|oracle| = {scale:.3f}): "
+          + ", ".join(f"{k}={v:.3e}" for k, v in row.items()))
+    assert torch.isfinite(r16).all() and torch.isfinite(p16).all() and torch.isfinite(pbf).all()
+    floor = 5e-3
+    assert row["prod_fp16_vs_oracle_fp32"] <= max(2.0 * row["ref_fp16_vs_oracle_fp32"], floor), row
+    assert row["prod_bf16_vs_oracle_fp32"] <= max(16.0 * row["ref_fp16_vs_oracle_fp32"], 8 * floor), row
+    assert row["prod_fp16_vs_ref_fp16"] <= max(3.0 * row["ref_fp16_vs_oracle_fp32"], floor), row
+
+
+# ------------------------------------------------------------------------------------------ full width
+def _full_width_pair(dtype):
+    """(product U-Net on CUDA in `dtype`, fp32 CPU oracle holding the SAME 16-bit-rounded weights)."""
+    from oracle.unet_ref import UNet2DConditionModelRef, UNetConfig as RefCfg
+    from tweediemix_b200.unet import TmxUNet2DConditionModel, UNetConfig, init_synthetic_
+    with torch.device("cuda"):
+        prod = TmxUNet2DConditionModel(UNetConfig.sdxl_base()).to(dtype)
+    init_synthetic_(prod, 7)
+    prod.requires_grad_(False).eval().finalize()
+    with torch.device("meta"):
+        orc = UNet2DConditionModelRef(RefCfg.sdxl())
+    orc = orc.to_empty(device="cpu")
+    orc.load_state_dict({k: v.detach().float().cpu() for k, v in prod.state_dict().items()})
+    return prod, orc.eval().requires_grad_(False)
+
+
+def _fw_inputs(batch, hw, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(1, 4, hw, hw, generator=g).repeat(batch, 1, 1, 1)
+    E = torch.randn(batch, 77, 2048, generator=g)
+    cond = {"text_embeds": torch.randn(batch, 1280, generator=g), "time_ids": torch.tensor([[1024, 1024, 0, 0, 1024, 1024]]).repeat(batch, 1)}
+    return x, E, cond
+
+
+TOL_FW = {torch.float16: 1.5e-2, torch.bfloat16: 6e-2}
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_full_width_sdxl_config_vs_oracle(dtype):
+    _build()
+    from tweediemix_b200 import utils_custom, utils_lora
+    from tweediemix_b200.synthetic import make_custom_concept, make_lora_concept
+    prod, orc = _full_width_pair(dtype)
+    window = torch.tensor([781, 761, 741])
+    results = {}
+
+    def compare(tag, batch, hw, t, lora_flag):
+        x, E, cond = _fw_inputs(batch, hw)
+        register_time_ref(orc, t, lora=True)
+        want = orc(x, t, E, cond)["sample"]
+        holder.unet = prod
+        hooks.register_time(holder, t)
+        got = prod(x.cuda(), t, E.cuda().to(dtype), {k: v.cuda() for k, v in cond.items()})["sample"]
+        rel = (got.float().cpu() - want).abs().max().item() / want.abs().max().item()
+        results[tag] = rel
+        print(f"PARITY full-width {tag} {dtype}: rel max|diff| = {rel:.3e}")
+        assert torch.isfinite(got).all() and rel <= TOL_FW[dtype], (tag, rel)
+
+    # ---- custom routing: row i+1 through concept i's K/V weights
+    hooks, holder = utils_custom, types.SimpleNamespace()
+    donors = [make_custom_concept(prod, 100 + i) for i in range(K)]
+    cpu_donors = [copy.deepcopy(d).float().cpu() for d in donors]
+    holder.unet = prod
+    for i, d in enumerate(donors):
+        setattr(holder, f"unet_{i}", d)
+    utils_custom.register_attention_control_efficient(holder, window, K)
+    register_custom_ref(orc, cpu_donors, window, K)
+    compare("custom routed b4 32x32", 4, 32, 761, False)
+    compare("custom unrouted b2 128x128", 2, 128, 801, False)          # outside the window; both GroupNorm paths, N = 4096 attention
+
+    # ---- LoRA routing on the same base weights (re-registering replaces the custom hooks on both sides)
+    hooks = utils_lora
+    prod.clear_text_cache()
+    ldonors = [make_lora_concept(prod, 200 + i, up_std=0.02) for i in range(K)]
+    holder = types.SimpleNamespace(unet=prod)
+    lora_sets = []
+    for i, d in enumerate(ldonors):
+        setattr(holder, f"unet_{i}", d)
+        ls = {}
+        for name, attn in prod.attention_modules():
+            proc = d.get_submodule(name).processor
+            ls[name] = {p: copy.deepcopy(getattr(proc, p)).float().cpu() for p in ("to_q_lora", "to_k_lora", "to_v_lora", "to_out_lora")}
+        lora_sets.append(ls)
+    utils_lora.register_attention_control_efficient(holder, window, K)
+    register_lora_ref(orc, lora_sets, window, K)
+    compare("lora routed b4 32x32", 4, 32, 761, True)
+    assert len(results) == 3
+
+
+# ------------------------------------------------------------------------------------------ K = 8, image batch
+def test_sampler_k8_vs_oracle():
+    _build()
+    k, n, res = 8, 5, 256
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = _extras(ref_unet, k, False)
+    orc = T._oracle_sampler(ref_unet, extra, False, n, res, k=k)
+    x0 = orc.initial_latent()
+    want = orc.sample_loop(x0.clone())
+    m = _gpu_product(ref_unet, extra, False, n, res, torch.float16, k=k)
+    got = m.sample_loop(x0.clone()).cpu()
+    rel = (got - want).abs().max().item() / want.abs().max().item()
+    print(f"PARITY K=8 sampler fp16: rel max|diff| = {rel:.3e}")
+    assert m.concept_num == 8 and m.n_forward_rows == orc.n_forward_rows and rel <= 3e-2
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_image_batch_equals_single_images_gpu(lora):
+    _build()
+    n, res = 5, 256
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = _extras(ref_unet, K, lora)
+    x = torch.randn(2, 4, res // 8, res // 8, generator=torch.Generator().manual_seed(4))
+    m = _gpu_product(ref_unet, extra, lora, n, res, torch.float16)
+    one = [m.sample_loop(x[i:i + 1].clone()).cpu() for i in range(2)]
+    both = m.sample_loop(x.clone()).cpu()
+    for i in range(2):
+        rel = (both[i:i + 1] - one[i]).abs().max().item() / one[i].abs().max().item()
+        assert rel <= 2e-2, rel           # the batch size changes which cuBLAS / cuDNN kernels run: 16-bit rounding noise only

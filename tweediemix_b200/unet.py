@@ -214,6 +214,11 @@ class TmxAttention(nn.Module):
         output) is added by the fused k6 kernel."""
         inner = self.heads * HEAD_DIM
         lora = routing if (routing is not None and routing.kind == "lora") else None
+        wdt = self.to_q.weight.dtype
+        if x.dtype != wdt:                      # a foreign caller under autocast hands fp32 LayerNorm outputs to 16-bit weights
+            x = x.to(wdt)
+        if encoder_hidden_states is not None and encoder_hidden_states.dtype != wdt:
+            encoder_hidden_states = encoder_hidden_states.to(wdt)
         if encoder_hidden_states is None:
             qkv = F.linear(x, self.packed_qkv())                                  # [B, N, 3*inner]
             if lora is not None:
@@ -237,6 +242,50 @@ class TmxAttention(nn.Module):
         if attention_mask is not None:
             raise RuntimeError("tmx attention has no mask path (the reference never passes one: utils_custom.py:95-99 is dead code)")
         return self.run(hidden_states, encoder_hidden_states, None, residual)
+
+
+class TmxAttentionView(TmxAttention):
+    """The tmx attention path over the parameters of a FOREIGN attention module — diffusers' ``Attention`` as the
+    reference patches it (``fusion_generation/utils_custom.py:113-158``, ``utils_lora.py:134-217``), or the oracle's
+    stand-in of it.  Nothing is copied except the packed q|k|v / k|v concatenations ``TmxAttention`` caches anyway; the
+    foreign module keeps its parameters, state-dict keys and attributes, and only gains an instance-level ``forward``
+    (installed by the hook layer) that runs here: cached routed K/V projection + tcgen05 SDPA through the C ABI."""
+
+    def __init__(self, foreign: nn.Module, is_cross: bool):
+        nn.Module.__init__(self)
+        inner = foreign.to_q.out_features
+        if inner != foreign.heads * HEAD_DIM:
+            raise RuntimeError(f"tmx attention supports head dim {HEAD_DIM} only (got {inner} / {foreign.heads} heads)")
+        self.heads, self.scale, self.is_cross = foreign.heads, float(foreign.scale), is_cross
+        self.to_q, self.to_k, self.to_v, self.to_out = foreign.to_q, foreign.to_k, foreign.to_v, foreign.to_out
+        self._w_qkv = self._w_kv = None
+        self._kv_cache = {}
+
+    @staticmethod
+    def of(module: nn.Module, is_cross: bool) -> TmxAttention:
+        """``module`` itself when it already is a ``TmxAttention``; else its (cached) view.  The view lives in the
+        module's ``__dict__`` so it is not registered as a sub-module (no extra state-dict keys)."""
+        if isinstance(module, TmxAttention):
+            return module
+        view = module.__dict__.get("_tmx_view")
+        if view is None:
+            view = TmxAttentionView(module, is_cross)
+            module.__dict__["_tmx_view"] = view
+        return view
+
+
+def iter_transformer_blocks(unet: nn.Module):
+    """(qualified name, block) for every transformer block that owns ``attn1`` / ``attn2`` — the product U-Net's own
+    iterator when it has one, else a walk of a diffusers-shaped tree (``unet.{down_blocks[1,2], mid_block,
+    up_blocks[0,1]}.attentions[j].transformer_blocks[k]``: the index maps the reference hard-codes at
+    ``utils_custom.py:113-117,126-157``, found here by structure instead of by literal depth tables)."""
+    own = getattr(unet, "transformer_blocks", None)
+    if callable(own):
+        yield from own()
+        return
+    for name, m in unet.named_modules():
+        if isinstance(getattr(m, "attn1", None), nn.Module) and isinstance(getattr(m, "attn2", None), nn.Module):
+            yield name, m
 
 
 class GEGLU(nn.Module):

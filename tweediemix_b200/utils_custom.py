@@ -18,7 +18,11 @@ Differences, all deliberate:
     run (3 concepts) and lets K != 3 work; ``gate=4`` restores the literal;
   * ``t in t_cond`` is evaluated against a host ``frozenset`` built once, not against a CUDA tensor
     (one device sync per module per step in the reference);
-  * ``unet_{i}`` may be a full U-Net or any module tree that has the ``attn2.to_k/to_v`` leaves.
+  * ``unet_{i}`` may be a full U-Net or any module tree that has the ``attn2.to_k/to_v`` leaves;
+  * ``model.unet`` may be the product's ``TmxUNet2DConditionModel`` OR a diffusers-shaped U-Net (the tree the reference
+    patches, ``utils_custom.py:113-158``): its ``Attention`` modules keep their parameters and get the same instance-level
+    ``forward`` — running the tmx kernels through a ``TmxAttentionView`` — so the hook layer drops into a diffusers pipeline
+    without replacing the U-Net (INTEGRATION.md path B; ``tests/test_adapter.py``).
 """
 from __future__ import annotations
 
@@ -28,7 +32,7 @@ import numpy as np
 import torch
 
 from .routing import CustomRouting
-from .unet import TmxAttention
+from .unet import TmxAttentionView, iter_transformer_blocks
 
 
 def seed_everything(seed):
@@ -40,7 +44,7 @@ def seed_everything(seed):
 
 
 def _cross_attentions(unet):
-    for name, blk in unet.transformer_blocks():
+    for name, blk in iter_transformer_blocks(unet):
         yield name + ".attn2", blk.attn2
 
 
@@ -66,7 +70,9 @@ def register_attention_control_efficient(model, t_cond, num_concepts, gate=None)
     window = as_window(t_cond)
     donors = [getattr(model, f"unet_{i}") for i in range(num_concepts)]
 
-    def install(attn: TmxAttention, name: str):
+    def install(attn, name: str):
+        # `attn` is the product's TmxAttention or a foreign diffusers-shaped Attention; `core` runs the arithmetic
+        core = TmxAttentionView.of(attn, is_cross=True)
         rows = [None]
         for i, donor in enumerate(donors):
             d = donor.get_submodule(name)
@@ -86,8 +92,8 @@ def register_attention_control_efficient(model, t_cond, num_concepts, gate=None)
             routed = (encoder_hidden_states is not None and attn.t in attn.fusion_window
                       and encoder_hidden_states.shape[0] == (gate if local is None else len(local)))
             if not routed:
-                return attn.run(x, encoder_hidden_states, None)
-            return attn.run(x, encoder_hidden_states, routing if local is None else routing.subset(local))
+                return core.run(x, encoder_hidden_states, None)
+            return core.run(x, encoder_hidden_states, routing if local is None else routing.subset(local))
 
         attn.forward = forward
 

@@ -17,12 +17,19 @@ Gate / window handling as in ``utils_custom`` (``gate=None`` -> ``num_concepts +
 from __future__ import annotations
 
 from .routing import LoRARouting, LoRARows
-from .unet import TmxAttention
+from .unet import TmxAttentionView, iter_transformer_blocks
 from .utils_custom import as_window, seed_everything  # noqa: F401  (same helper in both reference files)
 
 
+def _pair(layer, like):
+    """(down [r, in], up [out, r]) of a LoRA layer — the product's ``LoRALinearLayer`` or anything with ``.down`` /
+    ``.up`` Linear children (the reference's ``model_lora.LoRALinearLayer``) — on ``like``'s device / dtype."""
+    return (layer.down.weight.detach().to(device=like.device, dtype=like.dtype),
+            layer.up.weight.detach().to(device=like.device, dtype=like.dtype))
+
+
 def _all_attentions(unet):
-    for name, blk in unet.transformer_blocks():
+    for name, blk in iter_transformer_blocks(unet):
         yield name + ".attn2", blk.attn2
         yield name + ".attn1", blk.attn1
 
@@ -38,15 +45,17 @@ def register_attention_control_efficient(model, t_cond, num_concepts, gate=None)
     window = as_window(t_cond)
     donors = [getattr(model, f"unet_{i}") for i in range(num_concepts)]
 
-    def install(attn: TmxAttention, name: str):
+    def install(attn, name: str):
+        # `attn` is the product's TmxAttention or a foreign diffusers-shaped Attention; `core` runs the arithmetic
+        core = TmxAttentionView.of(attn, is_cross=name.endswith("attn2"))
         like = attn.to_q.weight
         rows = [None]
         for i, donor in enumerate(donors):
             proc = donor.get_submodule(name).processor
             for p in ("q", "k", "v", "out"):
                 setattr(attn, f"to_{p}_{i}_lora", getattr(proc, f"to_{p}_lora"))
-            rows.append(LoRARows(proc.to_q_lora.pair(like), proc.to_k_lora.pair(like),
-                                 proc.to_v_lora.pair(like), proc.to_out_lora.pair(like)))
+            rows.append(LoRARows(_pair(proc.to_q_lora, like), _pair(proc.to_k_lora, like),
+                                 _pair(proc.to_v_lora, like), _pair(proc.to_out_lora, like)))
         routing = LoRARouting(rows)
         attn.routing = routing
         attn.t_cond = t_cond
@@ -60,8 +69,8 @@ def register_attention_control_efficient(model, t_cond, num_concepts, gate=None)
             local = getattr(attn, "local_rows", None)        # concept-parallel: this rank's rows of the gate-sized batch
             routed = attn.t in attn.fusion_window and batch == (gate if local is None else len(local))
             if not routed:
-                return attn.run(x, encoder_hidden_states, None)
-            return attn.run(x, encoder_hidden_states, routing if local is None else routing.subset(local))
+                return core.run(x, encoder_hidden_states, None)
+            return core.run(x, encoder_hidden_states, routing if local is None else routing.subset(local))
 
         attn.forward = forward
 
