@@ -65,6 +65,9 @@ def main():
     ap.add_argument("--attn-variant", type=int, default=0, help="tmx_attn_set_variant() value (11 / 12 = one / two softmax threads per row)")
     ap.add_argument("--gn-variant", type=int, default=0, help="tmx_groupnorm_set_variant(): 0 fused cooperative, 1 two launches, 2 fused plain launch")
     ap.add_argument("--shapes", default="", help="comma-separated substrings; only shapes whose tag contains one are run (profiling aid)")
+    ap.add_argument("--compare", action="store_true",
+                    help="also time the same-box library kernels for the same shapes (measurement only, never a product dependency): "
+                         "F.scaled_dot_product_attention, flash-attn, F.group_norm+F.silu, F.layer_norm, F.linear (cuBLAS)")
     args = ap.parse_args()
     if args.gn_variant:
         from tweediemix_b200 import _lib
@@ -165,6 +168,67 @@ def main():
             us = timeit(lambda i: ops.tweedie_blend_ddim(x, e, m, 0.0438, 0.0518, 0.8, out=o), 1, args.reps)
             nbytes = imgs * (4 * 16384 * 8 + 16 * 16384 * 2) + 3 * 16384 * 4
             out.append(("blend", f"imgs{imgs}", us, nbytes / us / 1e3, "GB/s", hbm))
+    if want("routed"):
+        # k3: grouped tcgen05 GEMM (custom cross K/V, text-only: once per prompt set) and the rank-4 LoRA delta kernel
+        for d, H in [(1280, 20), (640, 10)]:
+            if not keep(f"kv_d{d}"):
+                continue
+            ehs = torch.randn(B, 77, 2048, device=dev, dtype=DT)
+            ws = [torch.randn(2 * d, 2048, device=dev, dtype=DT) * 0.02 for _ in range(B)]
+            y = torch.empty(B, 77, 2 * d, device=dev, dtype=DT)
+            us = timeit(lambda i: ops.routed_linear(ehs, ws, out=y), 1, args.reps)
+            out.append(("routed", f"gemm_kv_d{d}_M77_K2048_N{2 * d}", us, 2.0 * B * 77 * 2048 * 2 * d / us / 1e6, "TFLOP/s", tf))
+        for N, d, cnt in [(1024, 1280, 60), (4096, 640, 10)]:
+            for which, nseg, nout, per in [("qkv", 3, 3 * d, 1), ("q|out", 1, d, 3)]:
+                tag = f"lora_{which}_N{N}_d{d}"
+                if not keep(tag):
+                    continue
+                nb = nbuf_for(B * N * (d + 2 * nout) * 2)
+                xs = [torch.randn(B, N, d, device=dev, dtype=DT) for _ in range(nb)]
+                ys = [torch.randn(B, N, nout, device=dev, dtype=DT) for _ in range(nb)]
+                downs = [None] + [torch.randn(nseg * 4, d, device=dev, dtype=DT) * 0.25 for _ in range(B - 1)]
+                ups = [None] + [torch.randn(nout, 4, device=dev, dtype=DT) * 0.01 for _ in range(B - 1)]
+                us = timeit(lambda i: ops.routed_linear(xs[i], None, downs, ups, nseg=nseg, out=ys[i]), nb, args.reps)
+                nbytes = (B - 1) * N * (d + 2 * nout) * 2           # routed rows: read x, read + write y
+                out.append(("routed", f"{tag} x{cnt * per}", us, nbytes / us / 1e3, "GB/s", hbm))
+    if args.compare:
+        import torch.nn.functional as F
+        for N, H, cnt in [(4096, 10, 10), (1024, 20, 60)]:
+            qkv = [torch.randn(B, N, 3, H, 64, device=dev, dtype=DT) for _ in range(4)]
+            fl = 4.0 * B * H * N * N * 64
+            hv = [[t[:, :, j].permute(0, 2, 1, 3) for j in range(3)] for t in qkv]          # [B, H, N, 64] views, like the product reads them
+            try:
+                us = timeit(lambda i: F.scaled_dot_product_attention(hv[i][0], hv[i][1], hv[i][2]), 4, args.reps)
+                out.append(("cmp:sdpa", f"torch F.sdpa Nq{N}_H{H} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
+            except Exception as e:
+                print("cmp:sdpa failed:", str(e)[:200])
+            for backend in ("CUDNN_ATTENTION", "FLASH_ATTENTION"):
+                try:
+                    from torch.nn.attention import SDPBackend, sdpa_kernel
+                    with sdpa_kernel(getattr(SDPBackend, backend)):
+                        us = timeit(lambda i: F.scaled_dot_product_attention(hv[i][0], hv[i][1], hv[i][2]), 4, args.reps)
+                    out.append((f"cmp:sdpa", f"torch {backend} Nq{N}_H{H} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
+                except Exception as e:
+                    print(f"cmp:sdpa {backend} failed:", str(e)[:200])
+            try:
+                from flash_attn import flash_attn_func
+                us = timeit(lambda i: flash_attn_func(qkv[i][:, :, 0], qkv[i][:, :, 1], qkv[i][:, :, 2]), 4, args.reps)
+                out.append(("cmp:flash", f"flash-attn Nq{N}_H{H} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
+            except Exception as e:
+                print("cmp:flash failed:", str(e)[:200])
+        for C, HW, cnt in [(320, 16384, 5), (640, 4096, 9), (1280, 1024, 20)]:
+            h = int(HW ** 0.5)
+            nb = nbuf_for(B * C * HW * 4)
+            xs = [torch.randn(B, C, h, h, device=dev, dtype=DT).contiguous(memory_format=torch.channels_last) for _ in range(nb)]
+            g, b_ = torch.ones(C, device=dev, dtype=DT), torch.zeros(C, device=dev, dtype=DT)
+            us = timeit(lambda i: F.silu(F.group_norm(xs[i], 32, g, b_, 1e-5)), nb, args.reps)
+            out.append(("cmp:gn", f"torch group_norm+silu C{C}_HW{HW} x{cnt}", us, 2 * B * C * HW * 2 / us / 1e3, "GB/s", hbm))
+        for N, D, cnt in [(4096, 640, 30), (1024, 1280, 180)]:
+            nb = nbuf_for(B * N * D * 4)
+            xs = [torch.randn(B, N, D, device=dev, dtype=DT) for _ in range(nb)]
+            g, b_ = torch.ones(D, device=dev, dtype=DT), torch.zeros(D, device=dev, dtype=DT)
+            us = timeit(lambda i: F.layer_norm(xs[i], (D,), g, b_, 1e-5), nb, args.reps)
+            out.append(("cmp:ln", f"torch layer_norm N{N}_D{D} x{cnt}", us, 2 * B * N * D * 2 / us / 1e3, "GB/s", hbm))
     tot = {}
     for fam, tag, us, rate, unit, peak in out:
         print(f"{fam:10s} {tag:28s} {us:9.2f} us  {rate:9.1f} {unit:8s} {100 * rate / peak:5.1f}% of measured peak")

@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtmx.so")
+# $TMX_LIB_PATH selects another in-tree build of the same ABI (tuning variants compiled with other -D flags; see build.py)
+LIB_PATH = os.environ.get("TMX_LIB_PATH") or os.path.join(_HERE, "lib", "libtmx.so")
 
 F32, F16, BF16 = 0, 1, 2
 ACT_NONE, ACT_SILU = 0, 1

@@ -54,7 +54,16 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    """Compile csrc/*.cu and link libtmx.so (or `out`, a variant library built with $TMX_NVCC_EXTRA defines).  With
+    $TMX_LIB_PATH set the caller has chosen a prebuilt variant: nothing is rebuilt."""
+    if os.environ.get("TMX_LIB_PATH") and out is None:
+        path = os.environ["TMX_LIB_PATH"]
+        if not os.path.exists(path):
+            raise RuntimeError(f"TMX_LIB_PATH={path} does not exist")
+        return path
+    if out is not None:
+        return _build_variant(out, verbose)
     os.makedirs(LIBDIR, exist_ok=True)
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
@@ -88,5 +97,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def _build_variant(out: str, verbose: bool) -> str:
+    """A side build (objects under lib/<name>.objs/) that leaves libtmx.so and its stamp alone."""
+    objdir = out + ".objs"
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        procs.append((src, subprocess.Popen([_nvcc(), *_flags(), "-I", INCLUDE, "-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            print(o, file=sys.stderr)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    r = subprocess.run([_nvcc(), "-shared", "-o", out, *objs, "-cudart", "static", "-Xlinker", "--no-undefined", "-ldl", "-lpthread", "-lrt"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        print(r.stdout, file=sys.stderr)
+        raise RuntimeError("link failed")
+    shutil.rmtree(objdir, ignore_errors=True)
+    return out
+
+
 if __name__ == "__main__":
+    if "--out" in sys.argv:
+        print(build(out=os.path.abspath(sys.argv[sys.argv.index("--out") + 1]), verbose="--verbose" in sys.argv))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
