@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TMX_VERSION 100            /* 0.1.0 */
+#define TMX_VERSION 110            /* 0.1.1 */
 
 /* element types */
 #define TMX_F32  0
@@ -209,6 +209,40 @@ TMX_API int tmx_attn_set_variant(int nq);
 TMX_API int tmx_routed_linear_fwd(const void* x, const void* const* w, const void* const* lora_down,
                           const void* const* lora_up, void* y, int B, int M, int Kin, int Nout,
                           int rank, int nseg, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * k10 — dense projection with a fused epilogue (persistent tcgen05 GEMM, TMA in and out):
+ *   TMX_EPI_NONE  :  y[M, N]   = x[M, K] @ W[N, K]^T (+ bias[N]) (+ residual[M, N])
+ *   TMX_EPI_GEGLU :  y[M, N/2] = (a_v + bias_v) * gelu_erf(a_g + bias_g), where W (and bias) hold their rows INTERLEAVED in
+ *                    blocks of 32: rows [64j, 64j+32) = value rows 32j.., rows [64j+32, 64j+64) = gate rows 32j.. of the
+ *                    original [2F, K] GEGLU projection (value = first F rows, gate = last F rows)
+ * Replaces to_q / to_k / to_v / to_out[0] of the hooked attention forward (fusion_generation/utils_custom.py:63-89,106;
+ * utils_lora.py:65-79,113-121) with the residual add that follows in [D] BasicTransformerBlock folded in, and the [D] GEGLU
+ * feed-forward (proj -> value * gelu(gate) -> Linear -> + residual).
+ * Optional LoRA tail (utils_lora.py:65-79,113-119 as ONE extra K = 16 MMA step per tile): lora_t = dtype [M, 64] whose
+ * columns [0, 16) hold t = x @ down^T of each row's batch row (tmx_lora_t_fwd), lora_up = HOST array of lora_batch device
+ * pointers to dtype [N, 64] (columns [0, 16) = the up factors placed in their segment's slots, rest zero) or NULL entries
+ * for un-routed batch rows; batch row of x row m = m / lora_rows_per_batch (a multiple of 128).  lora_t == NULL: no tail.
+ * x : dtype [M, K], row stride ldx;  W : dtype [N, K] contiguous;  bias : fp32 [N] or NULL;  residual : dtype, row stride ldr,
+ * or NULL;  y row stride ldy.  K % 64 == 0, N % 8 == 0 (GEGLU: N % 64 == 0), strides multiples of 8.  fp32 accumulation, one
+ * rounding.  Algorithmic FLOPs: 2*M*N*K.
+ */
+#define TMX_EPI_NONE  0
+#define TMX_EPI_GEGLU 1
+TMX_API int tmx_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                   int M, int N, int K, int64_t ldx, int64_t ldr, int64_t ldy, int epilogue,
+                   const void* lora_t, const void* const* lora_up, int lora_rows_per_batch, int lora_batch,
+                   int dtype, void* stream);
+
+/* Tuning / test hook: force the tile width of tmx_linear_fwd (128 or 256 columns); 0 = heuristic. */
+TMX_API int tmx_linear_set_variant(int bn);
+
+/* t[b*M + m, q] = sum_k x[b, m, k] * down[b][q, k], q < sr = nseg*rank in {4, 8, 12, 16}: the A operand of the LoRA tail
+ * (model_lora.py:28-48 `down`).  x : dtype [B, M, K] with row stride ldx;  lora_down : HOST array of B device pointers to
+ * dtype [sr, K] (NULL = batch row not routed, its t rows are left untouched);  t : dtype [B*M, 64], zeroed once by the caller
+ * (only columns [0, sr) are written).  B <= 16. */
+TMX_API int tmx_lora_t_fwd(const void* x, const void* const* lora_down, void* t, int B, int M, int K, int64_t ldx,
+                   int sr, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,44 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg=1, out=
     return out
 
 
+def linear_supported(x, w):
+    from tweediemix_b200 import ops
+    return ops.GEMM_IMPL == "tmx" and x.shape[-1] % 64 == 0 and w.shape[0] % 8 == 0
+
+
+def linear(x, w, bias=None, *, residual=None, geglu=False, lora_tail=None, out=None):
+    N = w.shape[0]
+    y = x.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if lora_tail is not None:                                    # the K = 16 tail step: t[:, :16] @ up_ext[b][:, :16].T per batch row
+        t, ups, rpb = lora_tail
+        y2 = y.reshape(-1, N)
+        for b, u in enumerate(ups):
+            if u is not None:
+                y2[b * rpb:(b + 1) * rpb] += t[b * rpb:(b + 1) * rpb, :16].float() @ u[:, :16].float().t()
+        y = y2.reshape(y.shape)
+    if geglu:                                                    # rows interleaved in blocks of 32 value | 32 gate
+        z = y.reshape(*y.shape[:-1], N // 64, 2, 32)
+        y = (z[..., 0, :] * F.gelu(z[..., 1, :])).reshape(*y.shape[:-1], N // 2)
+    if residual is not None:
+        y = y + residual.float()
+    y = y.to(x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def lora_t(x, downs, sr):
+    B, M, K = x.shape
+    t = torch.zeros(B * M, 64, dtype=x.dtype, device=x.device)
+    for b, d in enumerate(downs):
+        if d is not None:
+            t[b * M:(b + 1) * M, :sr] = (x[b].float() @ d.float().t()).to(x.dtype)
+    return t
+
+
 def _mw(masks, weights, K, like):
     m = masks if masks is not None else torch.ones(K, 1, 1, 1, device=like.device)
     if weights is not None:
@@ -142,7 +180,11 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
     return res
 
 
+NAMES = ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention",
+         "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear", "linear", "lora_t", "linear_supported")
+
+
 def install(monkeypatch):
     from tweediemix_b200 import ops
-    for name in ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear"):
+    for name in NAMES:
         monkeypatch.setattr(ops, name, globals()[name])

@@ -29,7 +29,7 @@ def _worker(rank, world, port, lora, out_dir, max_group=None, n_imgs=1, k=None):
     try:
         import fake_ops
         from tweediemix_b200 import ops
-        for name in ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention", "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear"):
+        for name in fake_ops.NAMES:
             setattr(ops, name, getattr(fake_ops, name))
         import test_host_logic as T
         from oracle import synth

@@ -389,5 +389,16 @@ def test_routed_linear_weights_plus_lora_and_errors():
     torch.testing.assert_close(got.float(), want, rtol=2 ** -6, atol=6e-3)
     with pytest.raises(RuntimeError, match="multiple of 64"):
         o.routed_linear(torch.zeros(1, 4, 48, dtype=torch.bfloat16).cuda(), [torch.zeros(8, 48, dtype=torch.bfloat16).cuda()])
-    with pytest.raises(RuntimeError, match="B=17"):
-        o.routed_linear(torch.zeros(17, 4, 64, dtype=torch.bfloat16).cuda(), [torch.zeros(8, 64, dtype=torch.bfloat16).cuda()] * 17)
+    # more than 16 batch rows (K = 8 concepts x image batch 4 on one GPU = 36 rows): the front-end splits the batch into ABI
+    # calls of <= 16 rows; the ABI itself still refuses B = 17
+    B2 = 19
+    x2 = torch.randn(B2, 40, 64, generator=g).to(torch.bfloat16).cuda()
+    ws2 = [(torch.randn(24, 64, generator=g) / 8).to(torch.bfloat16).cuda() for _ in range(B2)]
+    d2 = [None if b % 3 == 0 else (torch.randn(r, 64, generator=g) / r).to(torch.bfloat16).cuda() for b in range(B2)]
+    u2 = [None if b % 3 == 0 else (torch.randn(24, r, generator=g) * 0.05).to(torch.bfloat16).cuda() for b in range(B2)]
+    torch.testing.assert_close(o.routed_linear(x2, ws2, d2, u2, nseg=1).float(), _routed_ref(x2, ws2, d2, u2, 1), rtol=2 ** -6, atol=6e-3)
+    from tweediemix_b200 import _lib
+    import ctypes as C
+    ptrs = (C.c_void_p * 17)(*[ws2[0].data_ptr()] * 17)
+    rc = _lib.load().tmx_routed_linear_fwd(x2.data_ptr(), ptrs, None, None, x2.data_ptr(), 17, 4, 64, 24, 0, 1, _lib.BF16, None)
+    assert rc == -2 and "B=17" in _lib.last_error()

@@ -157,3 +157,22 @@ def test_shared_scheduler_is_not_mutated(monkeypatch):
     m2 = Tweediemix(T._namespace(5, 128, False), comp, use_cuda_graphs=False)
     assert len(sched.timesteps) == 1000 and sched.alphas_cumprod.numel() == 1000
     assert m1.skip == m2.skip == 200 and m1._alpha_table == m2._alpha_table and len(m2._alpha_table) == 1001
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_library_gemm_path_matches_oracle(monkeypatch, lora):
+    """TMX_GEMM=cublas (library GEMM + stand-alone GEGLU / add+LayerNorm / LoRA-delta kernels) is the same function as the
+    default fused-epilogue path: both match the oracle sampler."""
+    fake_ops.install(monkeypatch)
+    from tweediemix_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_IMPL", "cublas")
+    n, res = 5, 128
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = _extras(ref_unet, T.K, lora)
+    prod = T._product_sampler(ref_unet, extra, lora, n, res)
+    orc = T._oracle_sampler(ref_unet, extra, lora, n, res)
+    x0 = orc.initial_latent()
+    want = orc.sample_loop(x0.clone())
+    prod.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else prod.init_fusion(int(n * 0.2))
+    got = prod.sample_loop(x0.clone())
+    assert (got - want).abs().max().item() < 1e-3

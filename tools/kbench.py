@@ -191,6 +191,44 @@ def main():
                 us = timeit(lambda i: ops.routed_linear(xs[i], None, downs, ups, nseg=nseg, out=ys[i]), nb, args.reps)
                 nbytes = (B - 1) * N * (d + 2 * nout) * 2           # routed rows: read x, read + write y
                 out.append(("routed", f"{tag} x{cnt * per}", us, nbytes / us / 1e3, "GB/s", hbm))
+    if want("linear"):
+        # k10 at the GEMM sites of one fused K=3 step (M = 4 rows x tokens): tile width auto / forced, and — with --compare —
+        # the library path it replaces (cuBLAS GEMM + the stand-alone epilogue kernel)
+        import torch.nn.functional as F
+        from tweediemix_b200 import _lib
+        lib = _lib.load()
+        sites = [("qkv", 4096, 3840, 1280, "", 60), ("out|q", 4096, 1280, 1280, "res", 180), ("ff1", 4096, 10240, 1280, "geglu", 60),
+                 ("ff2", 4096, 1280, 5120, "res", 60), ("qkv", 16384, 1920, 640, "", 10), ("out|q", 16384, 640, 640, "res", 30),
+                 ("ff1", 16384, 5120, 640, "geglu", 10), ("ff2", 16384, 640, 2560, "res", 10)]
+        for name, M, N, K, epi, cnt in sites:
+            tag = f"{name}_M{M}_N{N}_K{K}"
+            if not keep(tag):
+                continue
+            n_out = N // 2 if epi == "geglu" else N
+            nb = nbuf_for((M * K + M * n_out * 2) * 2)
+            xs = [torch.randn(M, K, device=dev, dtype=DT) for _ in range(nb)]
+            w = torch.randn(N, K, device=dev, dtype=DT) * K ** -0.5
+            bias = torch.randn(N, device=dev)
+            bias16 = bias.to(DT)
+            rs = [torch.randn(M, N, device=dev, dtype=DT) for _ in range(nb)] if epi == "res" else None
+            ys = [torch.empty(M, n_out, device=dev, dtype=DT) for _ in range(nb)]
+            fl = 2.0 * M * N * K
+            for bn in (0, 128, 256):
+                assert lib.tmx_linear_set_variant(bn) == 0
+                us = timeit(lambda i: ops.linear(xs[i], w, bias, residual=rs[i] if rs else None, geglu=epi == "geglu", out=ys[i]), nb, args.reps)
+                out.append(("linear" if bn == 0 else f"linear:bn{bn}", f"{tag}_{epi or 'bias'} x{cnt if bn == 0 else 0}", us, fl / us / 1e6, "TFLOP/s", tf))
+            lib.tmx_linear_set_variant(0)
+            if args.compare:
+                if epi == "geglu":
+                    fn = lambda i: ops.geglu(F.linear(xs[i], w, bias16), out=ys[i])
+                elif epi == "res":
+                    fn = lambda i: ops.residual_add(F.linear(xs[i], w, bias16), rs[i], out=ys[i])
+                else:
+                    fn = lambda i: F.linear(xs[i], w, bias16)
+                us = timeit(fn, nb, args.reps)
+                out.append(("cmp:cublas", f"cuBLAS + tmx epilogue kernel {tag}_{epi or 'bias'} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
+                us = timeit(lambda i: F.linear(xs[i], w, bias16), nb, args.reps)
+                out.append(("cmp:cublas-gemm", f"cuBLAS GEMM only {tag} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
     if args.compare:
         import torch.nn.functional as F
         for N, H, cnt in [(4096, 10, 10), (1024, 20, 60)]:

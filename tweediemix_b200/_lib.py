@@ -18,6 +18,7 @@ F32, F16, BF16 = 0, 1, 2
 ACT_NONE, ACT_SILU = 0, 1
 NCHW, NHWC = 0, 1
 ROUND_FP32, ROUND_REF = 0, 1
+EPI_NONE, EPI_GEGLU = 0, 1
 
 _vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 
@@ -41,6 +42,9 @@ SIGNATURES = {
     "tmx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _f, _i, _vp]),
     "tmx_attn_set_variant": (_i, [_i]),
     "tmx_routed_linear_fwd": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "tmx_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp, C.POINTER(_vp), _i, _i, _i, _vp]),
+    "tmx_linear_set_variant": (_i, [_i]),
+    "tmx_lora_t_fwd": (_i, [_vp, C.POINTER(_vp), _vp, _i, _i, _i, _i64, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -44,6 +44,7 @@ int sm_count() {
 int attn_init();      // attention.cu: function attributes + driver entry point for tensor maps
 int groupnorm_init(); // groupnorm.cu
 int routed_init();    // routed_linear.cu
+int linear_init();    // linear.cu
 
 }  // namespace tmx
 
@@ -66,6 +67,8 @@ extern "C" int tmx_init(int device) {
     rc = groupnorm_init();
     if (rc) return rc;
     rc = routed_init();
+    if (rc) return rc;
+    rc = linear_init();
     if (rc) return rc;
     g_inited[device] = 1;
     return TMX_OK;

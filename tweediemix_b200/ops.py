@@ -7,6 +7,7 @@ PyTorch implementation: non-CUDA tensors, unsupported shapes or a missing librar
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -371,6 +372,87 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg: int = 
             rc = _lib.load().tmx_routed_linear_fwd(_p(x[b0:]), wp, dp, up, _p(out[b0:]), nb, M, Kin, Nout, int(rank), int(nseg), _dt(x), _stream())
         _lib.check(rc, "tmx_routed_linear_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------ k10
+
+# 'tmx' (default): projections / feed-forward GEMMs of the transformer blocks run in the persistent tcgen05 kernel with
+# fused epilogues; 'cublas': library GEMM + separate elementwise kernels (kept for A/B measurements, tools/kbench.py).
+GEMM_IMPL = os.environ.get("TMX_GEMM", "tmx")
+
+
+def linear_supported(x, w) -> bool:
+    """Shapes on the kernel's tile grid (K % 64 == 0, N % 8 == 0, 16-bit CUDA tensors, uniform row stride)."""
+    return (GEMM_IMPL == "tmx" and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and w.dtype == x.dtype
+            and x.shape[-1] % 64 == 0 and w.shape[0] % 8 == 0 and x.is_contiguous() and w.is_contiguous())
+
+
+def geglu_interleave_index(F: int, device=None) -> torch.Tensor:
+    """Row permutation of a [2F, K] GEGLU projection (value rows then gate rows) into the kernel's layout: blocks of 64 rows =
+    32 value rows followed by their 32 gate rows."""
+    assert F % 32 == 0
+    j = torch.arange(F // 32, device=device)[:, None] * 32 + torch.arange(32, device=device)[None, :]      # [F/32, 32]
+    return torch.cat([j, j + F], dim=1).reshape(-1)
+
+
+def linear(x, w, bias=None, *, residual=None, geglu=False, lora_tail=None, out=None):
+    """y = x @ w.T (+ bias) (+ residual)   or, with ``geglu``, value * gelu(gate) of an INTERLEAVED projection (see
+    ``geglu_interleave_index``).  x [..., K] contiguous, w [N, K], bias fp32 [N]; residual / out [..., N_out].
+    ``lora_tail`` = (t [M, 64], ups: list of [N, 64] tensors or None per batch row, rows_per_batch)."""
+    _dev(x, w, bias, residual, out)
+    K = x.shape[-1]
+    N = w.shape[0]
+    M = x.numel() // K
+    n_out = N // 2 if geglu else N
+    assert w.shape[1] == K and x.is_contiguous() and w.is_contiguous() and w.dtype == x.dtype
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    if out is None:
+        out = torch.empty(*x.shape[:-1], n_out, dtype=x.dtype, device=x.device)
+    assert out.is_contiguous() and out.numel() == M * n_out and out.dtype == x.dtype
+    if residual is not None:
+        assert residual.dtype == x.dtype and residual.is_contiguous() and residual.numel() == M * N
+    t_ptr, up_arr, rpb, nb = None, None, 0, 0
+    if lora_tail is not None:
+        t, ups, rpb = lora_tail
+        nb = len(ups)
+        assert t.dtype == x.dtype and t.is_contiguous() and t.shape[-1] == 64 and t.numel() >= M * 64 and rpb * nb == M
+        for u in ups:
+            assert u is None or (u.dtype == x.dtype and u.is_contiguous() and tuple(u.shape) == (N, 64))
+        up_arr = (C.c_void_p * nb)(*[None if u is None else u.data_ptr() for u in ups])
+        t_ptr = t.data_ptr()
+    tag = f"M{M}_N{N}_K{K}" + ("_geglu" if geglu else "") + ("_res" if residual is not None else "") + ("_lora" if lora_tail is not None else "")
+    with _Launch("linear", 1, tag, 2.0 * M * N * K):
+        rc = _lib.load().tmx_linear_fwd(_p(x), _p(w), _p(bias), _p(residual), _p(out), M, N, K, K, N, n_out,
+                                        _lib.EPI_GEGLU if geglu else _lib.EPI_NONE, t_ptr, up_arr, int(rpb), int(nb), _dt(x), _stream())
+    _lib.check(rc, "tmx_linear_fwd")
+    return out
+
+
+_lora_t_buf = {}
+
+
+def lora_t(x, downs, sr: int):
+    """t = x[b] @ down[b].T per routed batch row into the shared [B*M, 64] operand buffer of the LoRA tail (columns beyond
+    ``sr`` stay zero; un-routed rows keep stale values the GEMM never reads)."""
+    _dev(x)
+    B, M, K = x.shape
+    assert x.is_contiguous() and len(downs) == B
+    key = (x.device.index, x.dtype, B * M)
+    t = _lora_t_buf.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("tmx: the LoRA tail buffer must be allocated before CUDA-graph capture; run the op once eagerly first")
+        t = _lora_t_buf[key] = torch.zeros(B * M, 64, dtype=x.dtype, device=x.device)
+    for d in downs:
+        assert d is None or (d.dtype == x.dtype and d.is_contiguous() and tuple(d.shape) == (sr, K))
+    for b0 in range(0, B, MAX_ROUTED_ROWS):
+        nb = min(MAX_ROUTED_ROWS, B - b0)
+        arr = (C.c_void_p * nb)(*[None if d is None else d.data_ptr() for d in downs[b0:b0 + nb]])
+        with _Launch("lora_t", 1, f"M{M}_K{K}", 0.0):
+            rc = _lib.load().tmx_lora_t_fwd(_p(x[b0:]), arr, t[b0 * M:].data_ptr(), nb, M, K, K, int(sr), _dt(x), _stream())
+        _lib.check(rc, "tmx_lora_t_fwd")
+    return t
 
 
 # ------------------------------------------------------------------------------------------ k1/k2

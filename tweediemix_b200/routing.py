@@ -100,6 +100,43 @@ class LoRARouting:
             self._lists[which] = got
         return got
 
+    def _ups_ext(self, which: str, nseg: int):
+        """Per batch row, the up factors of projection ``which`` as the B operand of the GEMM's K = 16 tail step: [Nout, 64]
+        with segment s's [seg, r] block in columns [s*r, (s+1)*r) of its own rows, zeros elsewhere."""
+        key = which + "_ext"
+        got = self._lists.get(key)
+        if got is None:
+            _, ups = self._factors(which)
+            got = []
+            for u in ups:
+                if u is None:
+                    got.append(None)
+                    continue
+                nout, r = u.shape
+                seg = nout // nseg
+                e = torch.zeros(nout, 64, dtype=u.dtype, device=u.device)
+                for s_ in range(nseg):
+                    e[s_ * seg:(s_ + 1) * seg, s_ * r:(s_ + 1) * r] = u[s_ * seg:(s_ + 1) * seg]
+                got.append(e)
+            self._lists[key] = got
+        return got
+
+    def tail(self, which: str, nseg: int, x):
+        """LoRA deltas of projection ``which`` as a fused tail of the projection GEMM (``ops.linear(lora_tail=...)``):
+        launches the skinny t = x @ down^T kernel and returns (t, ups, rows_per_batch) — or None when the shape is off the
+        fused path (token count per batch row not a multiple of the 128-row tile, rank layout beyond 16 slots), in which
+        case the caller adds the deltas with the stand-alone k3 kernel instead."""
+        self._check(x.shape[0])
+        downs, ups = self._factors(which)
+        routed = [d for d in downs if d is not None]
+        if not routed or LORA_IMPL != "k3":
+            return None
+        sr = routed[0].shape[0]
+        if x.dim() != 3 or x.shape[1] % 128 != 0 or sr not in (4, 8, 12, 16) or not x.is_contiguous() or x.shape[0] > 16:
+            return None
+        t = ops.lora_t(x, downs, sr)
+        return t, self._ups_ext(which, nseg), x.shape[1]
+
     def _add(self, which: str, nseg: int, x, y):
         """y[r] += segment-wise (x[r] @ down_r^T) @ up_r^T for every routed row r: ONE k3 launch for the whole batch."""
         self._check(x.shape[0])

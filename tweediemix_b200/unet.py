@@ -92,6 +92,34 @@ def _image(x3: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return x3.reshape(b, h, w, c).permute(0, 3, 1, 2)
 
 
+_F32_CACHE = {}
+
+
+def _f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Cached fp32 copy of a (16-bit) bias / affine parameter: the kernels take fp32 per-channel vectors."""
+    if p is None:
+        return None
+    key = (p.data_ptr(), p.numel(), p.dtype, p._version)
+    hit = _F32_CACHE.get(key)
+    if hit is None:
+        if len(_F32_CACHE) > 4096:
+            _F32_CACHE.clear()
+        hit = _F32_CACHE[key] = p.detach().float().contiguous()
+    return hit
+
+
+def _linear(x, weight, bias=None, residual=None, lora_tail=None):
+    """``x @ weight.T + bias (+ residual)``: the persistent tcgen05 GEMM with the bias / residual (/ LoRA tail) in its epilogue
+    when the shape is on its tile grid, else the library GEMM followed by the tmx residual-add kernel."""
+    if ops.linear_supported(x, weight):
+        return ops.linear(x, weight, _f32(bias), residual=residual, lora_tail=lora_tail)
+    assert lora_tail is None
+    y = F.linear(x, weight, bias)
+    if residual is not None:
+        y = ops.residual_add(y, residual, out=y)
+    return y
+
+
 class TmxGroupNorm(nn.GroupNorm):
     """``nn.GroupNorm`` parameters (state-dict names ``weight`` / ``bias``) executed by k4/k5."""
 
@@ -220,22 +248,26 @@ class TmxAttention(nn.Module):
         if encoder_hidden_states is not None and encoder_hidden_states.dtype != wdt:
             encoder_hidden_states = encoder_hidden_states.to(wdt)
         if encoder_hidden_states is None:
-            qkv = F.linear(x, self.packed_qkv())                                  # [B, N, 3*inner]
-            if lora is not None:
+            w = self.packed_qkv()
+            tail = lora.tail("qkv", 3, x) if lora is not None and ops.linear_supported(x, w) else None
+            qkv = _linear(x, w, lora_tail=tail)                                   # [B, N, 3*inner]
+            if lora is not None and tail is None:
                 lora.add_qkv_self(self, x, qkv)
             q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
         else:
-            q = F.linear(x, self.to_q.weight)
-            if lora is not None:
+            w = self.to_q.weight
+            tail = lora.tail("q", 1, x) if lora is not None and ops.linear_supported(x, w) else None
+            q = _linear(x, w, lora_tail=tail)
+            if lora is not None and tail is None:
                 lora.add_q(self, x, q)
             kv = self.cross_kv(encoder_hidden_states, routing)
             k, v = kv[..., :inner], kv[..., inner:]
         a = ops.attention(q, k, v, self.heads, self.scale)                        # [B, N, inner]
-        o = F.linear(a, self.to_out[0].weight, self.to_out[0].bias)
-        if lora is not None:
+        wo = self.to_out[0].weight
+        tail = lora.tail("out", 1, a) if lora is not None and ops.linear_supported(a, wo) else None
+        o = _linear(a, wo, self.to_out[0].bias, residual=residual, lora_tail=tail)   # bias, residual and LoRA delta in the epilogue
+        if lora is not None and tail is None:
             lora.add_out(self, a, o)
-        if residual is not None:
-            o = ops.residual_add(o, residual, out=o)
         return o
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, residual=None):
@@ -292,8 +324,19 @@ class GEGLU(nn.Module):
     def __init__(self, dim_in: int, dim_out: int):
         super().__init__()
         self.proj = nn.Linear(dim_in, dim_out * 2)
+        self._il = None                                       # (weight, fp32 bias) with value / gate rows interleaved for k10
+
+    def interleaved(self):
+        w = self.proj.weight
+        if self._il is None or self._il[0].device != w.device or self._il[0].dtype != w.dtype:
+            idx = ops.geglu_interleave_index(w.shape[0] // 2, w.device)
+            self._il = (w.detach()[idx].contiguous(), self.proj.bias.detach().float()[idx].contiguous())
+        return self._il
 
     def forward(self, x):
+        if ops.linear_supported(x, self.proj.weight) and self.proj.weight.shape[0] % 64 == 0:
+            w, b = self.interleaved()
+            return ops.linear(x, w, b, geglu=True)            # value * gelu(gate) in the GEMM epilogue: the [.., 8d] projection never reaches HBM
         return ops.geglu(self.proj(x))
 
 
@@ -302,8 +345,8 @@ class FeedForward(nn.Module):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
 
-    def forward(self, x):
-        return self.net[2](self.net[0](x))
+    def forward(self, x, residual=None):
+        return _linear(self.net[0](x), self.net[2].weight, self.net[2].bias, residual=residual)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -331,13 +374,13 @@ class BasicTransformerBlock(nn.Module):
         return p32
 
     @staticmethod
-    def _call_attn(attn: TmxAttention, x, ehs):
-        # A hooked module carries an instance-level ``forward`` with the reference's 3-argument
-        # signature (utils_custom.py:53); un-hooked modules go through nn.Module.__call__.
+    def _call_attn(attn: TmxAttention, x, ehs, residual=None):
+        # A hooked module carries an instance-level ``forward`` with the reference's 3-argument signature
+        # (utils_custom.py:53) plus the optional ``residual``; un-hooked modules go through nn.Module.__call__.
         hooked = attn.__dict__.get("forward")
         if hooked is None:
-            return attn(x, encoder_hidden_states=ehs, attention_mask=None)
-        return hooked(x, encoder_hidden_states=ehs, attention_mask=None)
+            return attn(x, encoder_hidden_states=ehs, attention_mask=None, residual=residual)
+        return hooked(x, encoder_hidden_states=ehs, attention_mask=None, residual=residual)
 
     def _add_norm(self, o, h, norm: Optional[nn.LayerNorm]):
         """h' = o + h (in o's storage) and, when a LayerNorm follows, n = norm(h') from the same kernel (k6c)."""
@@ -347,10 +390,17 @@ class BasicTransformerBlock(nn.Module):
         return ops.residual_add_layer_norm(o, h, g, b, norm.eps, h_out=o)
 
     def forward(self, h, encoder_hidden_states, n=None, next_norm: Optional[nn.LayerNorm] = None):
-        """``n`` = norm1(h) if the caller already has it (fused into the previous block's last add);
-        returns (h_out, next_norm(h_out) or None)."""
+        """``n`` = norm1(h) if the caller already has it; returns (h_out, next_norm(h_out) or None).
+        Fused path (k10): every residual add rides in the epilogue of the GEMM that produces the branch output, the
+        LayerNorm that follows is the stand-alone one-pass kernel.  Library-GEMM path: the add is fused with that
+        LayerNorm instead (k6c)."""
         if n is None:
             n = self._ln(self.norm1, h)
+        if ops.linear_supported(n, self.attn1.to_q.weight):
+            h = self._call_attn(self.attn1, n, None, residual=h)
+            h = self._call_attn(self.attn2, self._ln(self.norm2, h), encoder_hidden_states, residual=h)
+            h = self.ff(self._ln(self.norm3, h), residual=h)
+            return h, (self._ln(next_norm, h) if next_norm is not None else None)
         h, n = self._add_norm(self._call_attn(self.attn1, n, None), h, self.norm2)
         h, n = self._add_norm(self._call_attn(self.attn2, n, encoder_hidden_states), h, self.norm3)
         return self._add_norm(self.ff(n), h, next_norm)
@@ -369,13 +419,12 @@ class Transformer2DModel(nn.Module):
 
     def forward(self, x, encoder_hidden_states):
         _, _, hh, ww = x.shape
-        h = self.proj_in(_tokens(self.norm(x, silu=False)))
+        h = _linear(_tokens(self.norm(x, silu=False)), self.proj_in.weight, self.proj_in.bias)
         n = None
         blocks = self.transformer_blocks
         for i, blk in enumerate(blocks):
             h, n = blk(h, encoder_hidden_states, n, blocks[i + 1].norm1 if i + 1 < len(blocks) else None)
-        h = _image(self.proj_out(h), hh, ww)
-        return ops.residual_add(h, x, out=h)
+        return _image(_linear(h, self.proj_out.weight, self.proj_out.bias, residual=_tokens(x)), hh, ww)   # + x in the epilogue
 
 
 # =============================================================================== ResNet / sampling blocks
@@ -575,6 +624,8 @@ class TmxUNet2DConditionModel(nn.Module):
                 m.__dict__.pop("_b32", None)
             elif isinstance(m, TmxAttention):
                 m.drop_packed()
+            elif isinstance(m, GEGLU):
+                m._il = None
             elif isinstance(m, TmxGroupNorm):
                 m._w32 = m._b32 = None
             elif isinstance(m, nn.LayerNorm):
@@ -582,6 +633,7 @@ class TmxUNet2DConditionModel(nn.Module):
             elif isinstance(m, ResnetBlock2D):
                 m.__dict__.pop("_tail_bias", None)
         self._temb_w = self._temb_b = None
+        _F32_CACHE.clear()
         return self
 
     def refresh_text_cache(self):

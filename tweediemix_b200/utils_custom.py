@@ -85,15 +85,15 @@ def register_attention_control_efficient(model, t_cond, num_concepts, gate=None)
         attn.num_concepts = num_concepts
         attn.fusion_window = window
 
-        def forward(x, encoder_hidden_states=None, attention_mask=None):
+        def forward(x, encoder_hidden_states=None, attention_mask=None, residual=None):
             if attention_mask is not None:
                 raise RuntimeError("attention_mask is not supported (dead branch in the reference, utils_custom.py:95-99)")
             local = getattr(attn, "local_rows", None)        # concept-parallel: this rank's rows of the gate-sized batch
             routed = (encoder_hidden_states is not None and attn.t in attn.fusion_window
                       and encoder_hidden_states.shape[0] == (gate if local is None else len(local)))
             if not routed:
-                return core.run(x, encoder_hidden_states, None)
-            return core.run(x, encoder_hidden_states, routing if local is None else routing.subset(local))
+                return core.run(x, encoder_hidden_states, None, residual)
+            return core.run(x, encoder_hidden_states, routing if local is None else routing.subset(local), residual)
 
         attn.forward = forward
 

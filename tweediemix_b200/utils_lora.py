@@ -62,15 +62,15 @@ def register_attention_control_efficient(model, t_cond, num_concepts, gate=None)
         attn.num_concepts = num_concepts
         attn.fusion_window = window
 
-        def forward(x, encoder_hidden_states=None, attention_mask=None):
+        def forward(x, encoder_hidden_states=None, attention_mask=None, residual=None):
             if attention_mask is not None:
                 raise RuntimeError("attention_mask is not supported (dead branch in the reference, utils_lora.py:103-107)")
             batch = (x if encoder_hidden_states is None else encoder_hidden_states).shape[0]
             local = getattr(attn, "local_rows", None)        # concept-parallel: this rank's rows of the gate-sized batch
             routed = attn.t in attn.fusion_window and batch == (gate if local is None else len(local))
             if not routed:
-                return core.run(x, encoder_hidden_states, None)
-            return core.run(x, encoder_hidden_states, routing if local is None else routing.subset(local))
+                return core.run(x, encoder_hidden_states, None, residual)
+            return core.run(x, encoder_hidden_states, routing if local is None else routing.subset(local), residual)
 
         attn.forward = forward
 
