@@ -57,6 +57,33 @@ def main():
     ops.routed_linear(x, None, downs, ups, nseg=1, out=y)
     x2, y2 = rnd(2, 37, 64).to(bf), rnd(2, 37, 48).to(bf)
     ops.routed_linear(x2, None, [None, (rnd(12, 64) / 4).to(bf)], [None, (rnd(48, 4) * 0.05).to(bf)], nseg=3, out=y2)
+    # k10: ragged M / N tiles, both tile widths, bias + residual, GEGLU, LoRA tail (+ the t = x . down^T kernel)
+    from tweediemix_b200 import _lib
+    from tweediemix_b200.routing import LoRARouting
+    for bn in (128, 256):
+        assert _lib.load().tmx_linear_set_variant(bn) == 0
+        xa, wa = rnd(300, 192).to(bf), (rnd(328, 192) / 14).to(bf)
+        ba, ra = rnd(328), rnd(300, 328).to(bf)
+        ya = ops.linear(xa, wa, ba, residual=ra)
+        assert (ya.float() - (xa.float() @ wa.float().t() + ba + ra.float())).abs().max() < 6e-2
+        wg = (rnd(192, 64) / 8).to(bf)
+        idx = ops.geglu_interleave_index(96, dev)
+        yg = ops.linear(rnd(70, 64).to(bf), wg[idx].contiguous(), rnd(192)[idx].contiguous(), geglu=True)
+        assert yg.shape == (70, 96) and torch.isfinite(yg).all()
+        xl_ = rnd(3, 128, 64).to(bf)
+        dn = [None] + [(rnd(8, 64) / 4).to(bf) for _ in range(2)]
+        up = [None] + [(rnd(144, 4) * 0.05).to(bf) for _ in range(2)]
+        rt = LoRARouting.__new__(LoRARouting)
+        rt.rows, rt._lists, rt._subsets, rt.cache_tag = [None] * 3, {"w": (dn, up)}, {}, 0
+        wl = (rnd(144, 64) / 8).to(bf)
+        yl = ops.linear(xl_, wl, lora_tail=rt.tail("w", 2, xl_))
+        want = xl_.float() @ wl.float().t()
+        for b in (1, 2):
+            t = xl_[b].float() @ dn[b].float().t()
+            for s_ in range(2):
+                want[b, :, s_ * 72:(s_ + 1) * 72] += t[:, s_ * 4:(s_ + 1) * 4] @ up[b][s_ * 72:(s_ + 1) * 72].float().t()
+        assert (yl.float() - want).abs().max() < 6e-2
+    _lib.load().tmx_linear_set_variant(0)
     torch.cuda.synchronize()
     print("sanitize_small: all kernels ran")
 
