@@ -232,10 +232,16 @@ TMX_API int tmx_routed_linear_fwd(const void* x, const void* const* w, const voi
 TMX_API int tmx_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
                    int M, int N, int K, int64_t ldx, int64_t ldr, int64_t ldy, int epilogue,
                    const void* lora_t, const void* const* lora_up, int lora_rows_per_batch, int lora_batch,
-                   int dtype, void* stream);
+                   void* workspace, int dtype, void* stream);
 
-/* Tuning / test hook: force the tile width of tmx_linear_fwd (128 or 256 columns); 0 = heuristic. */
-TMX_API int tmx_linear_set_variant(int bn);
+/* Workspace of tmx_linear_fwd's split-K tail: when the tile count is not a multiple of the SM count, the tiles of the last,
+ * partly filled round are cut along K so that every SM works in it; the fp32 partial accumulators meet in `workspace` and are
+ * summed in a fixed order (bit-reproducible).  Allocate tmx_linear_workspace_bytes() once per stream of execution, zero its
+ * first 4 KiB ONCE (the kernels re-arm their counters), pass it to every call; NULL disables the split (whole tiles only). */
+TMX_API size_t tmx_linear_workspace_bytes(void);
+
+/* Tuning / test hook: tile width of tmx_linear_fwd (0 = heuristic, 128, 256), + 1000 to disable the split-K tail. */
+TMX_API int tmx_linear_set_variant(int v);
 
 /* t[b*M + m, q] = sum_k x[b, m, k] * down[b][q, k], q < sr = nseg*rank in {4, 8, 12, 16}: the A operand of the LoRA tail
  * (model_lora.py:28-48 `down`).  x : dtype [B, M, K] with row stride ldx;  lora_down : HOST array of B device pointers to

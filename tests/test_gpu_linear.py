@@ -32,7 +32,7 @@ SHAPES = [  # M, N, K
 ]
 
 
-@pytest.mark.parametrize("bn", [0, 128, 256])
+@pytest.mark.parametrize("bn", [0, 128, 256, 1000, 1256])      # + 1000: split-K tail disabled
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_linear_bias_residual(shape, dtype, bn):
@@ -54,9 +54,9 @@ def test_linear_bias_residual(shape, dtype, bn):
         _variant(0)
 
 
-@pytest.mark.parametrize("bn", [0, 128, 256])
+@pytest.mark.parametrize("bn", [0, 128, 256, 1256])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("shape", [(4096, 10240, 1280), (16384, 5120, 640), (256, 1024, 128), (100, 192, 64)])
+@pytest.mark.parametrize("shape", [(4096, 10240, 1280), (16384, 5120, 640), (256, 1024, 128), (100, 192, 64), (1024, 10240, 1280)])
 def test_linear_geglu_epilogue(shape, dtype, bn):
     """value * gelu_erf(gate) of an interleaved projection == the un-fused reference (projection rounded to 16 bits, then
     gated): [D] GEGLU.forward."""
@@ -78,9 +78,9 @@ def test_linear_geglu_epilogue(shape, dtype, bn):
         _variant(0)
 
 
-@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("bn", [0, 128, 256, 1256])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("B,Mb,N,K,nseg", [(4, 1024, 3840, 1280, 3), (4, 1024, 1280, 1280, 1), (3, 4096, 1920, 640, 3), (2, 128, 64, 64, 1)])
+@pytest.mark.parametrize("B,Mb,N,K,nseg", [(4, 1024, 3840, 1280, 3), (4, 1024, 1280, 1280, 1), (3, 4096, 1920, 640, 3), (2, 128, 64, 64, 1), (1, 1024, 1280, 1280, 1)])
 def test_linear_lora_tail(B, Mb, N, K, nseg, dtype, bn):
     """Rank-4 LoRA deltas as a K = 16 tail step of the GEMM (+ the skinny t = x . down^T kernel) == utils_lora.py:65-79:
     y[b] = x[b] W^T + per segment (x[b] down_s^T) up_s^T for routed rows, row 0 untouched."""
@@ -90,8 +90,9 @@ def test_linear_lora_tail(B, Mb, N, K, nseg, dtype, bn):
         r = 4
         g = torch.Generator().manual_seed(B * N)
         x, w = _mk((B, Mb, K), g, dtype), _mk((N, K), g, dtype, K ** -0.5)
-        downs = [None] + [_mk((nseg * r, K), g, dtype, 1.0 / r) for _ in range(B - 1)]
-        ups = [None] + [_mk((N, r), g, dtype, 0.05) for _ in range(B - 1)]
+        first = [None] if B > 1 else []                     # (B == 1: a rank that owns one ROUTED row, concept-parallel)
+        downs = first + [_mk((nseg * r, K), g, dtype, 1.0 / r) for _ in range(B - len(first))]
+        ups = first + [_mk((N, r), g, dtype, 0.05) for _ in range(B - len(first))]
         bias = torch.randn(N, generator=g).cuda()
         res = _mk((B, Mb, N), g, dtype)
         from tweediemix_b200.routing import LoRARouting
@@ -102,13 +103,35 @@ def test_linear_lora_tail(B, Mb, N, K, nseg, dtype, bn):
         got = o.linear(x, w, bias, residual=res, lora_tail=tail)
         seg = N // nseg
         want = x.float() @ w.float().t() + bias + res.float()
-        for b in range(1, B):
+        for b in range(len(first), B):
             t = (x[b].float() @ downs[b].float().t()).to(dtype).float()          # the tail consumes t rounded to 16 bits
             for s in range(nseg):
                 want[b, :, s * seg:(s + 1) * seg] += t[:, s * r:(s + 1) * r] @ ups[b][s * seg:(s + 1) * seg].float().t()
         torch.testing.assert_close(got.float(), want, rtol=RTOL[dtype], atol=8 * RTOL[dtype])
     finally:
         _variant(0)
+
+
+@pytest.mark.parametrize("shape", [(4096, 1280, 1280), (1024, 1280, 5120), (16384, 640, 640), (4096, 3840, 1280)])
+def test_split_k_tail_is_deterministic_and_rearms(shape):
+    """Shapes whose tile count is not a multiple of the SM count take the split-K tail (cooperative launch, fp32 partials summed in
+    slice order): repeated launches are bit-identical (fixed summation order, counters re-armed) and agree with the unsplit kernel
+    to fp32 accumulation-order round-off."""
+    o = _ops()
+    M, N, K = shape
+    g = torch.Generator().manual_seed(9)
+    x, w = _mk((M, K), g, torch.bfloat16), _mk((N, K), g, torch.bfloat16, K ** -0.5)
+    bias, res = torch.randn(N, generator=g).cuda(), _mk((M, N), g, torch.bfloat16)
+    _variant(0)
+    runs = [o.linear(x, w, bias, residual=res) for _ in range(4)]
+    assert all(torch.equal(runs[0], r) for r in runs[1:])
+    _variant(1000)
+    try:
+        whole = o.linear(x, w, bias, residual=res)
+    finally:
+        _variant(0)
+    torch.testing.assert_close(runs[0].float(), whole.float(), rtol=2 ** -7, atol=2 ** -6)
+    torch.testing.assert_close(runs[0].float(), x.float() @ w.float().t() + bias + res.float(), rtol=2 ** -7, atol=2 ** -5)
 
 
 def test_linear_rejects_bad_arguments():

@@ -42,7 +42,8 @@ SIGNATURES = {
     "tmx_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _f, _i, _vp]),
     "tmx_attn_set_variant": (_i, [_i]),
     "tmx_routed_linear_fwd": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "tmx_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp, C.POINTER(_vp), _i, _i, _i, _vp]),
+    "tmx_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp, C.POINTER(_vp), _i, _i, _vp, _i, _vp]),
+    "tmx_linear_workspace_bytes": (_sz, []),
     "tmx_linear_set_variant": (_i, [_i]),
     "tmx_lora_t_fwd": (_i, [_vp, C.POINTER(_vp), _vp, _i, _i, _i, _i64, _i, _i, _vp]),
 }

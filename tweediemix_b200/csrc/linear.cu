@@ -35,6 +35,8 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);   // 320
 constexpr int kSlab = kBM * 128;                 // one 64-column (128 B) slab of the staging tile: 16 KiB
 constexpr int kMaxBatchRows = 16;
+constexpr int kMaxTailTiles = 256;              // > any SM count: tail tiles < grid <= SMs
+constexpr int kMaxSplit = 8;
 
 template <int BN> struct Cfg {
     static constexpr int kBTile = BN * kBK * 2;                  // 16 / 32 KiB
@@ -144,10 +146,35 @@ struct Params {
     int rows_per_batch;        // LoRA tail: rows of x per batch row (multiple of 128)
     unsigned tail_mask;        // bit b set = batch row b carries LoRA factors
     const float* bias;         // [N] fp32 or null
+    // split-K tail: the tiles beyond the last full wave are cut `split` ways along K so that every SM has work in the last
+    // round; partial accumulators meet in an fp32 workspace and are summed in a FIXED order (deterministic)
+    int full_tiles;            // tiles computed whole (a multiple of the grid when split >= 2, else all tiles)
+    int split;                 // S >= 2, or 0
+    int tail_units;            // (tiles - full_tiles) * S
+    float* ws;                 // [tail tile][S][half][128 rows][128 cols] fp32
+    unsigned int* sync;        // [2][tail tile] arrival / done counters, zero between launches
 };
 
 // advance (stage, phase) of the K ring
 #define K10_NEXT(st, ph, NST) do { if (++(st) == (NST)) { (st) = 0; (ph) ^= 1u; } } while (0)
+
+// Work item i of this CTA: a whole tile (s < 0) or one K-slice of a tail tile.
+struct Item { int tile, k0, kn, s, tail_idx; };
+__device__ __forceinline__ bool get_item(const Params& p, int i, int KT, Item& it) {
+    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    if (t < p.full_tiles) { it.tile = t; it.k0 = 0; it.kn = KT; it.s = -1; it.tail_idx = 0; return true; }
+    if (p.split >= 2 && i == p.full_tiles / (int)gridDim.x && (int)blockIdx.x < p.tail_units) {
+        const int u = blockIdx.x;
+        it.tail_idx = u / p.split;
+        it.tile = p.full_tiles + it.tail_idx;
+        it.s = u - it.tail_idx * p.split;
+        const int base = KT / p.split, rem = KT - base * p.split;
+        it.k0 = it.s * base + (it.s < rem ? it.s : rem);
+        it.kn = base + (it.s < rem ? 1 : 0);
+        return true;
+    }
+    return false;
+}
 
 template <bool BF16, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -167,7 +194,6 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kRing + C::kStage + C::kBars * 8);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int KT = p.K / kBK;
-    const int total = p.MT * p.NT;
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
@@ -194,9 +220,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         // =========================================== TMA producer ===========================================
         int st = 0;
         uint32_t ph = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int nt = t / p.MT, mt = t - nt * p.MT;
-            for (int kt = 0; kt < KT; ++kt) {
+        Item it;
+        for (int i = 0; get_item(p, i, KT, it); ++i) {
+            const int nt = it.tile / p.MT, mt = it.tile - nt * p.MT;
+            for (int kt = it.k0; kt < it.k0 + it.kn; ++kt) {
                 mbar_wait(empty + 8 * st, ph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(full + 8 * st, kATile + C::kBTile);
@@ -205,7 +232,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 }
                 K10_NEXT(st, ph, NST);
             }
-            if (p.has_tail) {
+            if (p.has_tail && it.s <= 0) {                              // the LoRA step rides with the whole tile / the first K-slice
                 const int b = (mt * kBM) / p.rows_per_batch;
                 if ((p.tail_mask >> b) & 1u) {
                     mbar_wait(empty + 8 * st, ph ^ 1u);
@@ -222,14 +249,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         // =========================================== MMA issuer =============================================
         constexpr uint32_t idesc = make_idesc(BF16, kBM, BN);
         int st = 0;
-        uint32_t ph = 0, it = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-            const uint32_t a = it & 1u;
-            const int mt = t % p.MT;
-            mbar_wait(acc_empty + 8 * a, ((it >> 1) & 1u) ^ 1u);        // the epilogue has drained this accumulator stage
+        uint32_t ph = 0;
+        Item it;
+        for (int i = 0; get_item(p, i, KT, it); ++i) {
+            const uint32_t a = (uint32_t)i & 1u;
+            const int mt = it.tile % p.MT;
+            mbar_wait(acc_empty + 8 * a, (((uint32_t)i >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator stage
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * BN;
-            for (int kt = 0; kt < KT; ++kt) {
+            for (int kt = 0; kt < it.kn; ++kt) {
                 mbar_wait(full + 8 * st, ph);
                 tc_fence_after();
                 if (elect_one()) {
@@ -242,13 +270,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 }
                 K10_NEXT(st, ph, NST);
             }
-            if (p.has_tail) {
+            if (p.has_tail && it.s <= 0) {
                 const int b = (mt * kBM) / p.rows_per_batch;
                 if ((p.tail_mask >> b) & 1u) {                          // ONE K = 16 step: t[128 x 16] . up[b][BN x 16]^T
                     mbar_wait(full + 8 * st, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        umma_ss(d_tmem, desc_lo(sA + st * kATile), desc_lo(sB + st * C::kBTile), idesc, 1u);
+                        umma_ss(d_tmem, desc_lo(sA + st * kATile), desc_lo(sB + st * C::kBTile), idesc, it.kn > 0 ? 1u : 0u);
                         umma_commit(empty + 8 * st);
                     }
                     K10_NEXT(st, ph, NST);
@@ -269,104 +297,169 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         // this thread's 128-byte row of its slab, 16-byte chunks XOR-swizzled with the row (SWIZZLE_128B)
         const uint32_t c_row = sC + (geglu ? 0 : cg * kSlab) + row * 128;
         const uint32_t sw = (uint32_t)(row & 7);
-        uint32_t it = 0, nres = 0;
+        uint32_t nres = 0;
         bool first = true;
-        if (p.has_res && leader && (int)blockIdx.x < total) {            // residual of the first half
-            const int nt = blockIdx.x / p.MT, mt = blockIdx.x - nt * p.MT;
+
+        auto load_residual = [&](int nt, int mt, int h) {               // leader only: residual half -> staging tile
             mbar_expect_tx(res_full, 2 * kSlab);
-            tma_load_2d(sC, &tm_r, res_full, nt * BN, mt * kBM);
-            tma_load_2d(sC + kSlab, &tm_r, res_full, nt * BN + 64, mt * kBM);
-        }
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-            const uint32_t a = it & 1u;
-            const int nt = t / p.MT, mt = t - nt * p.MT;
-            mbar_wait(acc_full + 8 * a, (it >> 1) & 1u);
-            tc_fence_after();
-#pragma unroll 1
-            for (int h = 0; h < C::kHalves; ++h) {
-                uint32_t acc[64];
-                const uint32_t t_col = t_row + a * BN + h * 128 + cg * 64;
-                tmem_ld32(t_col, acc);
-                tmem_ld32(t_col + 32, acc + 32);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (h == C::kHalves - 1) {                               // accumulator stage fully read: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + 8 * a);
+            tma_load_2d(sC, &tm_r, res_full, nt * BN + h * 128, mt * kBM);
+            tma_load_2d(sC + kSlab, &tm_r, res_full, nt * BN + h * 128 + 64, mt * kBM);
+        };
+        // acc = this thread's 64 accumulator columns of half h of tile (nt, mt): bias / residual / GEGLU, one rounding, staging
+        // tile, TMA store; then (leader) prefetch the residual of the next whole-tile half this CTA will emit.
+        auto emit_half = [&](uint32_t (&acc)[64], int nt, int mt, int h, bool has_next, int nt2, int mt2, int h2) {
+            const int n_acc = nt * BN + h * 128 + cg * 64;              // first accumulator column of this thread's 64
+            if (!first) epi_bar();                                       // the leader has drained the previous TMA store (and issued the residual load)
+            first = false;
+            if (p.has_res) { mbar_wait(res_full, nres & 1u); ++nres; }
+            if (!geglu) {
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {                         // 8 columns = one 16-byte chunk
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[c8 * 8 + e]);
+                    const int n = n_acc + c8 * 8;
+                    if (p.bias != nullptr && n < p.N) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                    }
+                    const uint32_t addr = c_row + (((uint32_t)c8 ^ sw) << 4);
+                    if (p.has_res) {
+                        uint4 rv;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(addr));
+                        float r8[8];
+                        unpack8<T>(rv, r8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] += r8[e];
+                    }
+                    const uint4 v = pack8<T>(f);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                 }
-                const int n_acc = nt * BN + h * 128 + cg * 64;           // first accumulator column of this thread's 64
-                if (!first) epi_bar();                                   // the leader has drained the previous TMA store (and issued the residual load)
-                first = false;
-                if (p.has_res) { mbar_wait(res_full, nres & 1u); ++nres; }
+            } else {
+                // 64 accumulator columns = 32 value | 32 gate  ->  32 outputs at output column (n_acc / 2)
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float f[8];
+                    const int n = n_acc + c8 * 8;
+                    float bv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    if (p.bias != nullptr && n < p.N) {
+                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), v1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32)), g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 36));
+                        bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
+                        bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float v = __uint_as_float(acc[c8 * 8 + e]) + bv[e];
+                        const float g = __uint_as_float(acc[32 + c8 * 8 + e]) + bg[e];
+                        // the un-fused path rounds the projection to 16 bits before the gating kernel reads it
+                        f[e] = Pack2<T>::round(v) * gelu_erf(Pack2<T>::round(g));
+                    }
+                    const uint4 v = pack8<T>(f);
+                    const uint32_t addr = c_row + (((uint32_t)(cg * 4 + c8) ^ sw) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                }
+            }
+            fence_async_smem();                                          // generic-proxy writes -> visible to the TMA store
+            epi_bar();
+            if (leader) {
+                const int n0 = nt * BN + h * 128;                        // (a half that starts beyond N holds only zero padding)
                 if (!geglu) {
-#pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8) {                     // 8 columns = one 16-byte chunk
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[c8 * 8 + e]);
-                        const int n = n_acc + c8 * 8;
-                        if (p.bias != nullptr && n < p.N) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                        }
-                        const uint32_t addr = c_row + (((uint32_t)c8 ^ sw) << 4);
-                        if (p.has_res) {
-                            uint4 rv;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(addr));
-                            float r8[8];
-                            unpack8<T>(rv, r8);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] += r8[e];
-                        }
-                        const uint4 v = pack8<T>(f);
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-                    }
-                } else {
-                    // 64 accumulator columns = 32 value | 32 gate  ->  32 outputs at output column (n_acc / 2)
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        float f[8];
-                        const int n = n_acc + c8 * 8;
-                        float bv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                        if (p.bias != nullptr && n < p.N) {
-                            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), v1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32)), g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 36));
-                            bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
-                            bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float v = __uint_as_float(acc[c8 * 8 + e]) + bv[e];
-                            const float g = __uint_as_float(acc[32 + c8 * 8 + e]) + bg[e];
-                            // the un-fused path rounds the projection to 16 bits before the gating kernel reads it
-                            f[e] = Pack2<T>::round(v) * gelu_erf(Pack2<T>::round(g));
-                        }
-                        const uint4 v = pack8<T>(f);
-                        const uint32_t addr = c_row + (((uint32_t)(cg * 4 + c8) ^ sw) << 4);
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-                    }
+                    if (n0 < p.N) tma_store_2d(&tm_y, sC, n0, mt * kBM);
+                    if (n0 + 64 < p.N) tma_store_2d(&tm_y, sC + kSlab, n0 + 64, mt * kBM);
+                } else if (n0 < p.N) {
+                    tma_store_2d(&tm_y, sC, n0 >> 1, mt * kBM);
                 }
-                fence_async_smem();                                      // generic-proxy writes -> visible to the TMA store
-                epi_bar();
-                if (leader) {
-                    const int n0 = nt * BN + h * 128;                    // (a half that starts beyond N holds only zero padding)
-                    if (!geglu) {
-                        if (n0 < p.N) tma_store_2d(&tm_y, sC, n0, mt * kBM);
-                        if (n0 + 64 < p.N) tma_store_2d(&tm_y, sC + kSlab, n0 + 64, mt * kBM);
-                    } else if (n0 < p.N) {
-                        tma_store_2d(&tm_y, sC, n0 >> 1, mt * kBM);
+                tma_store_commit();
+                tma_store_wait_read();                                   // the staging tile may be overwritten
+                if (p.has_res && has_next) load_residual(nt2, mt2, h2);  // lands while the main loop of that tile runs
+            }
+        };
+
+        Item it, nx;
+        if (p.has_res && leader && get_item(p, 0, KT, it) && it.s < 0) load_residual(it.tile / p.MT, it.tile % p.MT, 0);
+        for (int i = 0; get_item(p, i, KT, it); ++i) {
+            const uint32_t a = (uint32_t)i & 1u;
+            const int nt = it.tile / p.MT, mt = it.tile - nt * p.MT;
+            mbar_wait(acc_full + 8 * a, ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            if (it.s < 0) {
+                // ---- whole tile
+                const bool more = get_item(p, i + 1, KT, nx) && nx.s < 0;
+#pragma unroll 1
+                for (int h = 0; h < C::kHalves; ++h) {
+                    uint32_t acc[64];
+                    const uint32_t t_col = t_row + a * BN + h * 128 + cg * 64;
+                    tmem_ld32(t_col, acc);
+                    tmem_ld32(t_col + 32, acc + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const bool last_half = h == C::kHalves - 1;
+                    if (last_half) {                                     // accumulator stage fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + 8 * a);
                     }
-                    tma_store_commit();
-                    tma_store_wait_read();                               // the staging tile may be overwritten
-                    if (p.has_res) {                                     // prefetch the residual of the NEXT half (it lands while the main loop of that tile runs)
-                        int t2 = t, h2 = h + 1;
-                        if (h2 == C::kHalves) { h2 = 0; t2 = t + gridDim.x; }
-                        if (t2 < total) {
-                            const int nt2 = t2 / p.MT, mt2 = t2 - nt2 * p.MT;
-                            mbar_expect_tx(res_full, 2 * kSlab);
-                            tma_load_2d(sC, &tm_r, res_full, nt2 * BN + h2 * 128, mt2 * kBM);
-                            tma_load_2d(sC + kSlab, &tm_r, res_full, nt2 * BN + h2 * 128 + 64, mt2 * kBM);
+                    emit_half(acc, nt, mt, h, !last_half || more, last_half ? nx.tile / p.MT : nt, last_half ? nx.tile % p.MT : mt, last_half ? 0 : h + 1);
+                }
+            } else {
+                // ---- one K-slice of a tail tile: park the partial accumulator in the workspace, then (slices 0 .. halves-1) sum
+                // the S partials of half h = s in slice order and emit it
+                float* wbase = p.ws + ((size_t)it.tail_idx * p.split + it.s) * (size_t)(C::kHalves * 128 * 128);
+#pragma unroll 1
+                for (int h = 0; h < C::kHalves; ++h) {
+                    uint32_t acc[64];
+                    const uint32_t t_col = t_row + a * BN + h * 128 + cg * 64;
+                    tmem_ld32(t_col, acc);
+                    tmem_ld32(t_col + 32, acc + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float4* dst = reinterpret_cast<float4*>(wbase + ((size_t)h * 128 + row) * 128 + cg * 64);
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; ++c4)
+                        __stcg(dst + c4, make_float4(__uint_as_float(acc[4 * c4]), __uint_as_float(acc[4 * c4 + 1]), __uint_as_float(acc[4 * c4 + 2]), __uint_as_float(acc[4 * c4 + 3])));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * a);
+                __threadfence();                                         // partials visible device-wide before the arrival below
+                epi_bar();
+                unsigned int* cnt = p.sync + it.tail_idx;
+                unsigned int* done = p.sync + kMaxTailTiles + it.tail_idx;
+                if (leader) atomicAdd(cnt, 1u);
+                if (it.s < C::kHalves) {
+                    const int h = it.s;
+                    if (leader) {
+                        if (p.has_res) load_residual(nt, mt, h);
+                        unsigned int cur, polls = 0;
+                        long long t0 = 0;
+                        while (true) {                                   // all S slices are co-resident (cooperative launch): bounded spin
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(cnt) : "memory");
+                            if (cur >= (unsigned)p.split) break;
+                            if ((++polls & 1023u) == 0) {
+                                const long long now = clock64();
+                                if (t0 == 0) t0 = now; else if (now - t0 > 4000000000LL) { atomicExch(&g_k10_timeout_flag, 2u); __trap(); }
+                            }
                         }
+                    }
+                    epi_bar();
+                    uint32_t acc[64];
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) acc[j] = 0u;
+                    const float* rbase = p.ws + (size_t)it.tail_idx * p.split * (size_t)(C::kHalves * 128 * 128) + ((size_t)h * 128 + row) * 128 + cg * 64;
+                    for (int s2 = 0; s2 < p.split; ++s2) {
+                        const float4* src = reinterpret_cast<const float4*>(rbase + (size_t)s2 * (C::kHalves * 128 * 128));
+#pragma unroll
+                        for (int c4 = 0; c4 < 16; ++c4) {
+                            const float4 v = __ldcg(src + c4);
+                            acc[4 * c4] = __float_as_uint(__uint_as_float(acc[4 * c4]) + v.x);
+                            acc[4 * c4 + 1] = __float_as_uint(__uint_as_float(acc[4 * c4 + 1]) + v.y);
+                            acc[4 * c4 + 2] = __float_as_uint(__uint_as_float(acc[4 * c4 + 2]) + v.z);
+                            acc[4 * c4 + 3] = __float_as_uint(__uint_as_float(acc[4 * c4 + 3]) + v.w);
+                        }
+                    }
+                    emit_half(acc, nt, mt, h, false, 0, 0, 0);
+                    if (leader) {                                        // last finaliser of the tile re-arms its counters for the next launch
+                        const unsigned nfinal = (unsigned)(p.split < C::kHalves ? p.split : C::kHalves);
+                        if (atomicAdd(done, 1u) == nfinal - 1u) { *cnt = 0u; *done = 0u; __threadfence(); }
                     }
                 }
             }
@@ -446,6 +539,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_force_bn = 0;     // tuning hook: 0 = heuristic, 128 / 256 = forced tile width
+static int g_split_mode = 0;   // tuning hook: 0 = split-K tail when a workspace is given, 1 = never
 
 // 2-D map over a row-major [rows, cols] 16-bit matrix with row stride ld (elements): dims (cols, rows), box (64, box_rows)
 static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows, bool bf16) {
@@ -460,14 +554,42 @@ static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
     return TMX_OK;
 }
 
-// Tile width: fewest (waves x tile time).  A 128-wide tile re-reads the x tile twice as often and runs the tensor pipe at the
-// shared-memory operand bandwidth, so it must win by more than kNarrowPenalty to be chosen.
-static int pick_bn(int M, int N) {
+// Split-K plan for `tiles` tiles on `sms` SMs: the r = tiles % sms tiles of the last, partly filled round are cut S ways along
+// K (S <= sms / r, <= kMaxSplit, >= 2 K blocks per slice) when a workspace is available.
+struct Plan { int full_tiles, split, tail_units, grid; double rounds; };
+static Plan make_plan(long long tiles, int KT, int sms, bool can_split) {
+    Plan pl;
+    const int q = (int)(tiles / sms), r = (int)(tiles % sms);
+    int S = 0;
+    if (can_split && r > 0 && g_split_mode != 1) {
+        S = sms / r;
+        if (S > kMaxSplit) S = kMaxSplit;
+        if (S > KT / 2) S = KT / 2;
+        if (S < 2) S = 0;
+    }
+    if (S >= 2) {
+        pl.full_tiles = q * sms; pl.split = S; pl.tail_units = r * S;
+        pl.grid = q > 0 ? sms : pl.tail_units;
+        pl.rounds = q + 1.0 / S + 0.12;                                // + workspace round trip and the finalisers' reads
+    } else {
+        pl.full_tiles = (int)tiles; pl.split = 0; pl.tail_units = 0;
+        pl.grid = (int)(tiles < sms ? tiles : sms);
+        pl.rounds = q + (r > 0 ? 1.0 : 0.0);
+    }
+    return pl;
+}
+
+// Tile width: fewest (rounds x tile time).  A 128-wide tile re-reads the x tile twice as often and runs the tensor pipe at
+// the shared-memory operand bandwidth — measured 0.835 of the 256-wide rate (profiles/r02b_kbench_linear.txt, ff1) — so it
+// only wins where it saves rounds.
+static int pick_bn(int M, int N, int KT, bool can_split) {
     if (g_force_bn == 128 || g_force_bn == 256) return g_force_bn;
-    const long long MT = (M + kBM - 1) / kBM, sms = sm_count();
-    auto cost = [&](int bn) { const long long tiles = MT * ((N + bn - 1) / bn); return (double)((tiles + sms - 1) / sms) * bn; };
-    constexpr double kNarrowPenalty = 1.12;
-    return cost(128) * kNarrowPenalty < cost(256) ? 128 : 256;
+    if (N <= 128) return 128;
+    const long long MT = (M + kBM - 1) / kBM;
+    const int sms = sm_count();
+    const double c128 = make_plan(MT * ((N + 127) / 128), KT, sms, can_split).rounds * 128 / 0.835;
+    const double c256 = make_plan(MT * ((N + 255) / 256), KT, sms, can_split).rounds * 256;
+    return c128 < c256 ? 128 : 256;
 }
 
 }  // namespace k10
@@ -497,16 +619,24 @@ int linear_init() {
 using namespace tmx;
 using namespace tmx::k10;
 
-extern "C" int tmx_linear_set_variant(int bn) {
-    TMX_REQUIRE(bn == 0 || bn == 128 || bn == 256, TMX_EINVAL, "linear_set_variant: tile width must be 0 (auto), 128 or 256");
+extern "C" int tmx_linear_set_variant(int v) {
+    // v = tile width (0 auto, 128, 256) + 1000 to disable the split-K tail
+    const int bn = v % 1000, nosplit = v / 1000;
+    TMX_REQUIRE(v >= 0 && (bn == 0 || bn == 128 || bn == 256) && nosplit <= 1, TMX_EINVAL, "linear_set_variant: 0 | 128 | 256 (+ 1000 = no split-K tail)");
     g_force_bn = bn;
+    g_split_mode = nosplit;
     return TMX_OK;
+}
+
+extern "C" size_t tmx_linear_workspace_bytes(void) {
+    // counters (2 x kMaxTailTiles words, zeroed ONCE by the caller) + fp32 partial tiles: at most one K-slice per SM, 128 KiB each
+    return 4096 + (size_t)256 * 2 * 128 * 128 * sizeof(float);
 }
 
 extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
                               int M, int N, int K, int64_t ldx, int64_t ldr, int64_t ldy, int epilogue,
                               const void* lora_t, const void* const* lora_up, int lora_rows_per_batch, int lora_batch,
-                              int dtype, void* stream) {
+                              void* workspace, int dtype, void* stream) {
     TMX_REQUIRE(x && w && y, TMX_EINVAL, "linear: null pointer");
     TMX_REQUIRE(M > 0 && N > 0 && K > 0, TMX_EINVAL, "linear: non-positive size");
     TMX_REQUIRE(dtype == TMX_F16 || dtype == TMX_BF16, TMX_EDTYPE, "linear: dtype %d unsupported (fp16/bf16 only)", dtype);
@@ -515,18 +645,23 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
     TMX_REQUIRE(N % 8 == 0 && (epilogue != TMX_EPI_GEGLU || N % 64 == 0), TMX_ESHAPE, "linear: N=%d must be a multiple of 8 (64 with the GEGLU epilogue)", N);
     const int n_out = epilogue == TMX_EPI_GEGLU ? N / 2 : N;
     TMX_REQUIRE(ldx >= K && ldy >= n_out && ldx % 8 == 0 && ldy % 8 == 0, TMX_ESHAPE, "linear: bad row strides ldx=%lld ldy=%lld", (long long)ldx, (long long)ldy);
-    TMX_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias) && aligned16(residual), TMX_EALIGN, "linear: 16-byte alignment");
+    TMX_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias) && aligned16(residual) && aligned16(workspace), TMX_EALIGN, "linear: 16-byte alignment");
     TMX_REQUIRE(!(residual && epilogue == TMX_EPI_GEGLU), TMX_EINVAL, "linear: the GEGLU epilogue takes no residual");
     TMX_REQUIRE(!residual || (ldr >= N && ldr % 8 == 0), TMX_ESHAPE, "linear: bad residual row stride %lld", (long long)ldr);
     if (int rc = require_init()) return rc;
     const bool bf16 = dtype == TMX_BF16;
-    const int BN = pick_bn(M, N);
+    const int KT = K / kBK;
+    const int BN = pick_bn(M, N, KT, workspace != nullptr);
 
     Params p;
     p.M = M; p.N = N; p.K = K;
     p.MT = (M + kBM - 1) / kBM; p.NT = (N + BN - 1) / BN;
     p.epilogue = epilogue; p.has_res = residual != nullptr; p.bias = bias;
     p.has_tail = 0; p.rows_per_batch = 1; p.tail_mask = 0;
+    const Plan pl = make_plan((long long)p.MT * p.NT, KT, sm_count(), workspace != nullptr);
+    p.full_tiles = pl.full_tiles; p.split = pl.split; p.tail_units = pl.tail_units;
+    p.sync = reinterpret_cast<unsigned int*>(workspace);
+    p.ws = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 4096) : nullptr;
     CUtensorMap mx, mw, my, mr, mt;
     UpMaps ups;
     if (int rc = encode2d(&mx, x, (uint64_t)K, (uint64_t)M, (uint64_t)ldx, kBM, bf16)) return rc;
@@ -550,17 +685,16 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
         p.has_tail = p.tail_mask != 0;
         p.rows_per_batch = lora_rows_per_batch;
     }
-    const long long tiles = (long long)p.MT * p.NT;
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     cudaStream_t st = (cudaStream_t)stream;
-    if (BN == 256) {
-        if (bf16) linear_kernel<true, 256><<<grid, kThreads, Cfg<256>::kSmem, st>>>(mx, mw, my, mr, mt, ups, p);
-        else      linear_kernel<false, 256><<<grid, kThreads, Cfg<256>::kSmem, st>>>(mx, mw, my, mr, mt, ups, p);
-    } else {
-        if (bf16) linear_kernel<true, 128><<<grid, kThreads, Cfg<128>::kSmem, st>>>(mx, mw, my, mr, mt, ups, p);
-        else      linear_kernel<false, 128><<<grid, kThreads, Cfg<128>::kSmem, st>>>(mx, mw, my, mr, mt, ups, p);
+    const void* fn = BN == 256 ? (bf16 ? (const void*)linear_kernel<true, 256> : (const void*)linear_kernel<false, 256>)
+                               : (bf16 ? (const void*)linear_kernel<true, 128> : (const void*)linear_kernel<false, 128>);
+    const size_t smem = BN == 256 ? Cfg<256>::kSmem : Cfg<128>::kSmem;
+    void* args[] = {&mx, &mw, &my, &mr, &mt, &ups, &p};
+    if (pl.split >= 2) {
+        // the K-slices of a tail tile wait for each other: the grid (<= one CTA per SM) must be co-resident
+        return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(pl.grid), dim3(kThreads), args, smem, st), "linear_kernel cooperative launch");
     }
-    return check_cuda(cudaGetLastError(), "linear_kernel launch");
+    return check_cuda(cudaLaunchKernel(fn, dim3(pl.grid), dim3(kThreads), args, smem, st), "linear_kernel launch");
 }
 
 extern "C" int tmx_lora_t_fwd(const void* x, const void* const* lora_down, void* t, int B, int M, int K, int64_t ldx,

@@ -381,6 +381,20 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg: int = 
 GEMM_IMPL = os.environ.get("TMX_GEMM", "tmx")
 
 
+_lin_ws = {}
+
+
+def _linear_workspace(dev: int) -> torch.Tensor:
+    """Split-K tail workspace of k10 (counters + fp32 partial tiles), one per device, allocated on first use; the kernels
+    leave the counters at zero, launches on one stream are serialised, so one buffer serves every call."""
+    ws = _lin_ws.get(dev)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("tmx: the GEMM workspace must be allocated before CUDA-graph capture; run the op once eagerly first")
+        ws = _lin_ws[dev] = torch.zeros(_lib.load().tmx_linear_workspace_bytes(), dtype=torch.uint8, device=f"cuda:{dev}")
+    return ws
+
+
 def linear_supported(x, w) -> bool:
     """Shapes on the kernel's tile grid (K % 64 == 0, N % 8 == 0, 16-bit CUDA tensors, uniform row stride)."""
     return (GEMM_IMPL == "tmx" and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and w.dtype == x.dtype
@@ -422,9 +436,11 @@ def linear(x, w, bias=None, *, residual=None, geglu=False, lora_tail=None, out=N
         up_arr = (C.c_void_p * nb)(*[None if u is None else u.data_ptr() for u in ups])
         t_ptr = t.data_ptr()
     tag = f"M{M}_N{N}_K{K}" + ("_geglu" if geglu else "") + ("_res" if residual is not None else "") + ("_lora" if lora_tail is not None else "")
+    ws = _linear_workspace(x.device.index)
     with _Launch("linear", 1, tag, 2.0 * M * N * K):
         rc = _lib.load().tmx_linear_fwd(_p(x), _p(w), _p(bias), _p(residual), _p(out), M, N, K, K, N, n_out,
-                                        _lib.EPI_GEGLU if geglu else _lib.EPI_NONE, t_ptr, up_arr, int(rpb), int(nb), _dt(x), _stream())
+                                        _lib.EPI_GEGLU if geglu else _lib.EPI_NONE, t_ptr, up_arr, int(rpb), int(nb),
+                                        _p(ws), _dt(x), _stream())
     _lib.check(rc, "tmx_linear_fwd")
     return out
 
