@@ -3,12 +3,15 @@
 Tolerances.  The oracle is fp32 end to end; the product computes in fp16 / bf16 with fp32 accumulation
 (what the reference itself does under ``autocast(fp16)``), so agreement is bounded by
 the 16-bit roundings of ~600 chained layers, not by the kernels (those are pinned tightly in
-test_gpu_kernels.py / test_gpu_attention.py).  Stated bounds, relative to max|oracle output|:
-  U-Net forward (tiny width, 70 transformer blocks): fp16 <= 1.5e-2, bf16 <= 6e-2
-  hooked / routed forward: same
-  10-step sampler latent (max-abs and L2, relative): fp16 <= 5e-2, bf16 <= 1.5e-1 — measured on B200:
-  fp16 ~1e-2, bf16 ~8e-2; the seeded random U-Net amplifies 8-bit-mantissa rounding more than real
-  SDXL weights would, and the fp32-oracle comparison is the honest one (SURVEY §7 'parity budget')
+test_gpu_kernels.py / test_gpu_attention.py / test_gpu_linear.py).  The yardstick is MEASURED: the reference's own
+execution mode (oracle U-Net + oracle hooks, fp16 weights, CUDA, torch.autocast(fp16)) deviates from the fp32 oracle by
+1.16e-2 (custom) / 1.17e-2 (LoRA) of max|latent| after the 10-step run of tests/test_gpu_parity.py; the product lands at
+7.6e-3 / 7.2e-3 in fp16 and 6.8e-2 / 7.0e-2 in bf16 (B200, profiles/r02b_pytest_gpu.txt).  Stated bounds, relative to
+max|oracle output|:
+  U-Net forward (tiny width, 70 transformer blocks): fp16 <= 1.5e-2, bf16 <= 6e-2; hooked / routed forward: same
+  10-step sampler latent (max-abs and L2, relative): fp16 <= 2.5e-2 (= 2x the reference's own fp16 deviation),
+  bf16 <= 1.5e-1 (13x: the bf16 mantissa is 3 bits shorter; the seeded random U-Net amplifies rounding more than real
+  SDXL weights would, and the fp32-oracle comparison is the honest one — SURVEY §7 'parity budget')
 CUDA-graph replay vs eager: bit-identical.  GEGLU kernel: one output rounding.
 """
 import argparse
@@ -25,7 +28,7 @@ pytestmark = pytest.mark.gpu
 
 K = 3
 TOL_FWD = {torch.float16: 1.5e-2, torch.bfloat16: 6e-2}
-TOL_LOOP = {torch.float16: 5e-2, torch.bfloat16: 1.5e-1}
+TOL_LOOP = {torch.float16: 2.5e-2, torch.bfloat16: 1.5e-1}
 
 
 def _build():

@@ -134,7 +134,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : K10_R8(r, 0), K10_R8(r, 8), K10_R8(r, 16), K10_R8(r, 24) : "r"(taddr) : "memory");
 }
 
-__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : K10_R8(r, 0), K10_R8(r, 8) : "r"(taddr) : "memory");
+}
+
+// Exact-GELU gate 0.5 g (1 + erf(g / sqrt 2)) with erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the 2^-9 /
+// 2^-12 rounding of the 16-bit output): one MUFU.RCP + one MUFU.EX2 + 8 FMA instead of erff's ~40 instructions — the GEGLU
+// epilogue of a K = 640 tile has only ~5000 clk before the next accumulator is ready.
+__device__ __forceinline__ float gelu_erf(float g) {
+    const float x = fabsf(g) * 0.70710678118654752f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = poly * t * exp2f(-1.4426950408889634f * x * x);     // 1 - erf(|x|)
+    const float one_plus_erf = g >= 0.f ? 2.f - e : e;                   // 1 + erf(x) without cancellation for negative g
+    return 0.5f * g * one_plus_erf;
+}
 
 struct UpMaps { CUtensorMap m[kMaxBatchRows]; };
 
@@ -305,59 +325,73 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
             tma_load_2d(sC, &tm_r, res_full, nt * BN + h * 128, mt * kBM);
             tma_load_2d(sC + kSlab, &tm_r, res_full, nt * BN + h * 128 + 64, mt * kBM);
         };
-        // acc = this thread's 64 accumulator columns of half h of tile (nt, mt): bias / residual / GEGLU, one rounding, staging
-        // tile, TMA store; then (leader) prefetch the residual of the next whole-tile half this CTA will emit.
-        auto emit_half = [&](uint32_t (&acc)[64], int nt, int mt, int h, bool has_next, int nt2, int mt2, int h2) {
+        // One 128-column half of tile (nt, mt): the thread's 64 accumulator columns arrive 16 at a time through `fetch16(col, v)`
+        // (TMEM for a whole tile, the summed workspace partials for a split tile — few live registers either way), then bias /
+        // residual / GEGLU, one rounding, staging tile, TMA store; the leader then prefetches the residual of the next whole-tile
+        // half this CTA will emit.
+        auto emit_half = [&](auto&& fetch16, int nt, int mt, int h, bool has_next, int nt2, int mt2, int h2) {
             const int n_acc = nt * BN + h * 128 + cg * 64;              // first accumulator column of this thread's 64
             if (!first) epi_bar();                                       // the leader has drained the previous TMA store (and issued the residual load)
             first = false;
             if (p.has_res) { mbar_wait(res_full, nres & 1u); ++nres; }
             if (!geglu) {
+#pragma unroll 1
+                for (int q4 = 0; q4 < 4; ++q4) {                         // 16 columns = two 16-byte chunks
+                    uint32_t v[16];
+                    fetch16(q4 * 16, v);
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {                         // 8 columns = one 16-byte chunk
-                    float f[8];
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        float f[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[c8 * 8 + e]);
-                    const int n = n_acc + c8 * 8;
-                    if (p.bias != nullptr && n < p.N) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c2 * 8 + e]);
+                        const int c8 = q4 * 2 + c2;
+                        const int n = n_acc + c8 * 8;
+                        if (p.bias != nullptr && n < p.N) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        const uint32_t addr = c_row + (((uint32_t)c8 ^ sw) << 4);
+                        if (p.has_res) {
+                            uint4 rv;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(addr));
+                            float r8[8];
+                            unpack8<T>(rv, r8);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] += r8[e];
+                        }
+                        const uint4 o = pack8<T>(f);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
-                    const uint32_t addr = c_row + (((uint32_t)c8 ^ sw) << 4);
-                    if (p.has_res) {
-                        uint4 rv;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(addr));
-                        float r8[8];
-                        unpack8<T>(rv, r8);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] += r8[e];
-                    }
-                    const uint4 v = pack8<T>(f);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                 }
             } else {
-                // 64 accumulator columns = 32 value | 32 gate  ->  32 outputs at output column (n_acc / 2)
+                // 64 accumulator columns = 32 value | 32 gate  ->  32 outputs at output column (n_acc / 2), 16 per pass
+#pragma unroll 1
+                for (int q2 = 0; q2 < 2; ++q2) {
+                    uint32_t v[16], g[16];
+                    fetch16(q2 * 16, v);
+                    fetch16(32 + q2 * 16, g);
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    float f[8];
-                    const int n = n_acc + c8 * 8;
-                    float bv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    if (p.bias != nullptr && n < p.N) {
-                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), v1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32)), g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 36));
-                        bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
-                        bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
-                    }
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        float f[8];
+                        const int n = n_acc + q2 * 16 + c2 * 8;
+                        float bv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        if (p.bias != nullptr && n < p.N) {
+                            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), v1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32)), g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 36));
+                            bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
+                            bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
+                        }
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float v = __uint_as_float(acc[c8 * 8 + e]) + bv[e];
-                        const float g = __uint_as_float(acc[32 + c8 * 8 + e]) + bg[e];
-                        // the un-fused path rounds the projection to 16 bits before the gating kernel reads it
-                        f[e] = Pack2<T>::round(v) * gelu_erf(Pack2<T>::round(g));
+                        for (int e = 0; e < 8; ++e) {
+                            const float a = __uint_as_float(v[c2 * 8 + e]) + bv[e];
+                            const float b = __uint_as_float(g[c2 * 8 + e]) + bg[e];
+                            // the un-fused path rounds the projection to 16 bits before the gating kernel reads it
+                            f[e] = Pack2<T>::round(a) * gelu_erf(Pack2<T>::round(b));
+                        }
+                        const uint4 o = pack8<T>(f);
+                        const uint32_t addr = c_row + (((uint32_t)(cg * 4 + q2 * 2 + c2) ^ sw) << 4);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
-                    const uint4 v = pack8<T>(f);
-                    const uint32_t addr = c_row + (((uint32_t)(cg * 4 + c8) ^ sw) << 4);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                 }
             }
             fence_async_smem();                                          // generic-proxy writes -> visible to the TMA store
@@ -376,46 +410,47 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
             }
         };
 
+        // workspace layout of one (tail tile, slice, half): [epilogue warp][float4 index within the thread's 64 columns][lane],
+        // so that every warp-wide access is one contiguous 512-byte run
+        constexpr size_t kHalfF4 = (size_t)kEpiWarps * 16 * 32;          // float4 per half = 128 x 128 fp32
         Item it, nx;
+        nx.tile = 0;
         if (p.has_res && leader && get_item(p, 0, KT, it) && it.s < 0) load_residual(it.tile / p.MT, it.tile % p.MT, 0);
         for (int i = 0; get_item(p, i, KT, it); ++i) {
             const uint32_t a = (uint32_t)i & 1u;
             const int nt = it.tile / p.MT, mt = it.tile - nt * p.MT;
             mbar_wait(acc_full + 8 * a, ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
+            const uint32_t t_acc = t_row + a * BN + cg * 64;
             if (it.s < 0) {
                 // ---- whole tile
                 const bool more = get_item(p, i + 1, KT, nx) && nx.s < 0;
 #pragma unroll 1
                 for (int h = 0; h < C::kHalves; ++h) {
-                    uint32_t acc[64];
-                    const uint32_t t_col = t_row + a * BN + h * 128 + cg * 64;
-                    tmem_ld32(t_col, acc);
-                    tmem_ld32(t_col + 32, acc + 32);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     const bool last_half = h == C::kHalves - 1;
-                    if (last_half) {                                     // accumulator stage fully read: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty + 8 * a);
-                    }
-                    emit_half(acc, nt, mt, h, !last_half || more, last_half ? nx.tile / p.MT : nt, last_half ? nx.tile % p.MT : mt, last_half ? 0 : h + 1);
+                    const uint32_t t_col = t_acc + h * 128;
+                    emit_half([&](int col, uint32_t (&v)[16]) { tmem_ld16(t_col + col, v); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); },
+                              nt, mt, h, !last_half || more, last_half ? nx.tile / p.MT : nt, last_half ? nx.tile % p.MT : mt, last_half ? 0 : h + 1);
                 }
+                tc_fence_before();                                       // accumulator stage fully read: hand it back to the MMA warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * a);
             } else {
                 // ---- one K-slice of a tail tile: park the partial accumulator in the workspace, then (slices 0 .. halves-1) sum
                 // the S partials of half h = s in slice order and emit it
-                float* wbase = p.ws + ((size_t)it.tail_idx * p.split + it.s) * (size_t)(C::kHalves * 128 * 128);
+                float4* wbase = reinterpret_cast<float4*>(p.ws) + ((size_t)it.tail_idx * p.split + it.s) * (C::kHalves * kHalfF4) + (size_t)ew * 16 * 32 + lane;
 #pragma unroll 1
                 for (int h = 0; h < C::kHalves; ++h) {
-                    uint32_t acc[64];
-                    const uint32_t t_col = t_row + a * BN + h * 128 + cg * 64;
-                    tmem_ld32(t_col, acc);
-                    tmem_ld32(t_col + 32, acc + 32);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float4* dst = reinterpret_cast<float4*>(wbase + ((size_t)h * 128 + row) * 128 + cg * 64);
+#pragma unroll 1
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint32_t v[16];
+                        tmem_ld16(t_acc + h * 128 + q4 * 16, v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c4 = 0; c4 < 16; ++c4)
-                        __stcg(dst + c4, make_float4(__uint_as_float(acc[4 * c4]), __uint_as_float(acc[4 * c4 + 1]), __uint_as_float(acc[4 * c4 + 2]), __uint_as_float(acc[4 * c4 + 3])));
+                        for (int c4 = 0; c4 < 4; ++c4)
+                            __stcg(wbase + h * kHalfF4 + (size_t)(q4 * 4 + c4) * 32,
+                                   make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3])));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -441,22 +476,27 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                         }
                     }
                     epi_bar();
-                    uint32_t acc[64];
+                    const float4* rbase = reinterpret_cast<const float4*>(p.ws) + (size_t)it.tail_idx * p.split * (C::kHalves * kHalfF4) + h * kHalfF4 + (size_t)ew * 16 * 32 + lane;
+                    const int S = p.split;
+                    emit_half([&](int col, uint32_t (&v)[16]) {
+                                  float4 acc4[4];
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) acc[j] = 0u;
-                    const float* rbase = p.ws + (size_t)it.tail_idx * p.split * (size_t)(C::kHalves * 128 * 128) + ((size_t)h * 128 + row) * 128 + cg * 64;
-                    for (int s2 = 0; s2 < p.split; ++s2) {
-                        const float4* src = reinterpret_cast<const float4*>(rbase + (size_t)s2 * (C::kHalves * 128 * 128));
+                                  for (int c4 = 0; c4 < 4; ++c4) acc4[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                  for (int s2 = 0; s2 < S; ++s2) {       // fixed summation order: bit-reproducible
+                                      const float4* src = rbase + (size_t)s2 * (C::kHalves * kHalfF4) + (size_t)(col >> 2) * 32;
 #pragma unroll
-                        for (int c4 = 0; c4 < 16; ++c4) {
-                            const float4 v = __ldcg(src + c4);
-                            acc[4 * c4] = __float_as_uint(__uint_as_float(acc[4 * c4]) + v.x);
-                            acc[4 * c4 + 1] = __float_as_uint(__uint_as_float(acc[4 * c4 + 1]) + v.y);
-                            acc[4 * c4 + 2] = __float_as_uint(__uint_as_float(acc[4 * c4 + 2]) + v.z);
-                            acc[4 * c4 + 3] = __float_as_uint(__uint_as_float(acc[4 * c4 + 3]) + v.w);
-                        }
-                    }
-                    emit_half(acc, nt, mt, h, false, 0, 0, 0);
+                                      for (int c4 = 0; c4 < 4; ++c4) {
+                                          const float4 w = __ldcg(src + c4 * 32);
+                                          acc4[c4].x += w.x; acc4[c4].y += w.y; acc4[c4].z += w.z; acc4[c4].w += w.w;
+                                      }
+                                  }
+#pragma unroll
+                                  for (int c4 = 0; c4 < 4; ++c4) {
+                                      v[4 * c4] = __float_as_uint(acc4[c4].x); v[4 * c4 + 1] = __float_as_uint(acc4[c4].y);
+                                      v[4 * c4 + 2] = __float_as_uint(acc4[c4].z); v[4 * c4 + 3] = __float_as_uint(acc4[c4].w);
+                                  }
+                              },
+                              nt, mt, h, false, 0, 0, 0);
                     if (leader) {                                        // last finaliser of the tile re-arms its counters for the next launch
                         const unsigned nfinal = (unsigned)(p.split < C::kHalves ? p.split : C::kHalves);
                         if (atomicAdd(done, 1u) == nfinal - 1u) { *cnt = 0u; *done = 0u; __threadfence(); }
