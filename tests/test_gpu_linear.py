@@ -27,12 +27,12 @@ def _mk(shape, g, dtype, scale=1.0):
 
 
 SHAPES = [  # M, N, K
-    (4096, 3840, 1280), (4096, 1280, 1280), (4096, 1280, 5120), (16384, 1920, 640), (16384, 640, 640), (16384, 640, 2560),
+    (4096, 1280, 5120), (4096, 3840, 1280), (4096, 1280, 1280), (4096, 1280, 5120), (16384, 1920, 640), (16384, 640, 640), (16384, 640, 2560),
     (1024, 1280, 1280), (128, 128, 64), (200, 136, 128), (77, 2560, 2048), (300, 72, 192), (20000, 256, 64),
 ]
 
 
-@pytest.mark.parametrize("bn", [0, 128, 256, 1000, 1256])      # + 1000: split-K tail disabled
+@pytest.mark.parametrize("bn", [0, 128, 192, 256, 1000, 1256])      # + 1000: split-K tail disabled
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_linear_bias_residual(shape, dtype, bn):
@@ -78,7 +78,7 @@ def test_linear_geglu_epilogue(shape, dtype, bn):
         _variant(0)
 
 
-@pytest.mark.parametrize("bn", [0, 128, 256, 1256])
+@pytest.mark.parametrize("bn", [0, 128, 192, 256, 1256])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("B,Mb,N,K,nseg", [(4, 1024, 3840, 1280, 3), (4, 1024, 1280, 1280, 1), (3, 4096, 1920, 640, 3), (2, 128, 64, 64, 1), (1, 1024, 1280, 1280, 1)])
 def test_linear_lora_tail(B, Mb, N, K, nseg, dtype, bn):
@@ -112,8 +112,9 @@ def test_linear_lora_tail(B, Mb, N, K, nseg, dtype, bn):
         _variant(0)
 
 
-@pytest.mark.parametrize("shape", [(4096, 1280, 1280), (1024, 1280, 5120), (16384, 640, 640), (4096, 3840, 1280)])
-def test_split_k_tail_is_deterministic_and_rearms(shape):
+@pytest.mark.parametrize("bn", [0, 128, 256])
+@pytest.mark.parametrize("shape", [(4096, 1280, 5120), (1024, 1280, 5120), (16384, 640, 2560), (2048, 1280, 5120), (4096, 1280, 1280)])
+def test_split_k_tail_is_deterministic_and_rearms(shape, bn):
     """Shapes whose tile count is not a multiple of the SM count take the split-K tail (cooperative launch, fp32 partials summed in
     slice order): repeated launches are bit-identical (fixed summation order, counters re-armed) and agree with the unsplit kernel
     to fp32 accumulation-order round-off."""
@@ -122,10 +123,10 @@ def test_split_k_tail_is_deterministic_and_rearms(shape):
     g = torch.Generator().manual_seed(9)
     x, w = _mk((M, K), g, torch.bfloat16), _mk((N, K), g, torch.bfloat16, K ** -0.5)
     bias, res = torch.randn(N, generator=g).cuda(), _mk((M, N), g, torch.bfloat16)
-    _variant(0)
+    _variant(bn)
     runs = [o.linear(x, w, bias, residual=res) for _ in range(4)]
     assert all(torch.equal(runs[0], r) for r in runs[1:])
-    _variant(1000)
+    _variant(1000 + bn)
     try:
         whole = o.linear(x, w, bias, residual=res)
     finally:

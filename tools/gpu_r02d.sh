@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 pass D (1 GPU): k10 after the epilogue restructure (16-column passes, coalesced split-K workspace, A&S erf).
-TAG=${1:-r02d}
+TAG=${1:-r02e}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 python -m tweediemix_b200.build > $OUT/build.log 2>&1
@@ -11,7 +11,7 @@ timeout 900 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > $OUT/bench.
 timeout 900 python bench.py --config 2 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_lora.json 2> $OUT/bench_lora.err; echo "bench lora (fused) rc=$?"; tail -3 $OUT/bench_lora.err
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob("gpurun_out/r02d/bench*.json")):
+for f in sorted(glob.glob("gpurun_out/$TAG/bench*.json")):
     try:
         d=json.load(open(f)); print(f, "value", round(d["value"],4), "e2e", round(d["e2e"]["value"],4), "step_ms", round(d["per_denoise_step_ms"],2), {k: round(v,2) for k,v in d["fused_step_tmx_kernel_ms"].items()})
     except Exception as e: print(f, "unreadable", e)

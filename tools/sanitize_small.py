@@ -60,7 +60,7 @@ def main():
     # k10: ragged M / N tiles, both tile widths, bias + residual, GEGLU, LoRA tail (+ the t = x . down^T kernel)
     from tweediemix_b200 import _lib
     from tweediemix_b200.routing import LoRARouting
-    for bn in (128, 256):
+    for bn in (128, 192, 256):
         assert _lib.load().tmx_linear_set_variant(bn) == 0
         xa, wa = rnd(300, 192).to(bf), (rnd(328, 192) / 14).to(bf)
         ba, ra = rnd(328), rnd(300, 328).to(bf)
@@ -83,7 +83,10 @@ def main():
             for s_ in range(2):
                 want[b, :, s_ * 72:(s_ + 1) * 72] += t[:, s_ * 4:(s_ + 1) * 4] @ up[b][s_ * 72:(s_ + 1) * 72].float().t()
         assert (yl.float() - want).abs().max() < 6e-2
+    xs_, ws_ = rnd(256, 2560).to(bf), (rnd(256, 2560) / 50).to(bf)          # 2 tiles, K = 2560: split-K tail (cooperative launch)
     _lib.load().tmx_linear_set_variant(0)
+    ys_ = ops.linear(xs_, ws_, rnd(256), residual=rnd(256, 256).to(bf))
+    assert torch.isfinite(ys_).all()
     torch.cuda.synchronize()
     print("sanitize_small: all kernels ran")
 

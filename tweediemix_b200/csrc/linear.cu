@@ -39,14 +39,14 @@ constexpr int kMaxTailTiles = 256;              // > any SM count: tail tiles < 
 constexpr int kMaxSplit = 8;
 
 template <int BN> struct Cfg {
-    static constexpr int kBTile = BN * kBK * 2;                  // 16 / 32 KiB
-    static constexpr int kStages = BN == 256 ? 4 : 5;
-    static constexpr int kRing = kStages * (kATile + kBTile);    // 192 / 160 KiB
+    static constexpr int kBTile = BN * kBK * 2;                  // 16 / 24 / 32 KiB
+    static constexpr int kStages = BN == 128 ? 5 : 4;
+    static constexpr int kRing = kStages * (kATile + kBTile);    // 160 / 160 / 192 KiB
     static constexpr int kStage = 2 * kSlab;                     // staging tile: 128 rows x 128 columns, 32 KiB
     static constexpr int kBars = 2 * kStages + 4 + 1;
     static constexpr int kSmem = 1024 + kRing + kStage + kBars * 8 + 16;
-    static constexpr int kTmemCols = 2 * BN;                     // two accumulator stages
-    static constexpr int kHalves = BN / 128;
+    static constexpr int kTmemCols = BN == 128 ? 256 : 512;      // two accumulator stages of BN columns (power of two)
+    static constexpr int kHalves = (BN + 127) / 128;             // BN = 192: the second half holds 64 columns
 };
 
 __device__ unsigned int g_k10_timeout_flag = 0;
@@ -196,7 +196,7 @@ __device__ __forceinline__ bool get_item(const Params& p, int i, int KT, Item& i
     return false;
 }
 
-template <bool BF16, int BN>
+template <bool BF16, int BN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
               const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r,
@@ -321,86 +321,25 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         bool first = true;
 
         auto load_residual = [&](int nt, int mt, int h) {               // leader only: residual half -> staging tile
-            mbar_expect_tx(res_full, 2 * kSlab);
+            const bool two = h * 128 + 64 < BN;                          // (BN = 192: the second half is one slab)
+            mbar_expect_tx(res_full, two ? 2 * kSlab : kSlab);
             tma_load_2d(sC, &tm_r, res_full, nt * BN + h * 128, mt * kBM);
-            tma_load_2d(sC + kSlab, &tm_r, res_full, nt * BN + h * 128 + 64, mt * kBM);
+            if (two) tma_load_2d(sC + kSlab, &tm_r, res_full, nt * BN + h * 128 + 64, mt * kBM);
         };
-        // One 128-column half of tile (nt, mt): the thread's 64 accumulator columns arrive 16 at a time through `fetch16(col, v)`
-        // (TMEM for a whole tile, the summed workspace partials for a split tile — few live registers either way), then bias /
-        // residual / GEGLU, one rounding, staging tile, TMA store; the leader then prefetches the residual of the next whole-tile
-        // half this CTA will emit.
-        auto emit_half = [&](auto&& fetch16, int nt, int mt, int h, bool has_next, int nt2, int mt2, int h2) {
-            const int n_acc = nt * BN + h * 128 + cg * 64;              // first accumulator column of this thread's 64
+        // ---- pieces shared by the two epilogue styles
+        auto pre_half = [&]() {
             if (!first) epi_bar();                                       // the leader has drained the previous TMA store (and issued the residual load)
             first = false;
             if (p.has_res) { mbar_wait(res_full, nres & 1u); ++nres; }
-            if (!geglu) {
-#pragma unroll 1
-                for (int q4 = 0; q4 < 4; ++q4) {                         // 16 columns = two 16-byte chunks
-                    uint32_t v[16];
-                    fetch16(q4 * 16, v);
-#pragma unroll
-                    for (int c2 = 0; c2 < 2; ++c2) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c2 * 8 + e]);
-                        const int c8 = q4 * 2 + c2;
-                        const int n = n_acc + c8 * 8;
-                        if (p.bias != nullptr && n < p.N) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                        }
-                        const uint32_t addr = c_row + (((uint32_t)c8 ^ sw) << 4);
-                        if (p.has_res) {
-                            uint4 rv;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(addr));
-                            float r8[8];
-                            unpack8<T>(rv, r8);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] += r8[e];
-                        }
-                        const uint4 o = pack8<T>(f);
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-                    }
-                }
-            } else {
-                // 64 accumulator columns = 32 value | 32 gate  ->  32 outputs at output column (n_acc / 2), 16 per pass
-#pragma unroll 1
-                for (int q2 = 0; q2 < 2; ++q2) {
-                    uint32_t v[16], g[16];
-                    fetch16(q2 * 16, v);
-                    fetch16(32 + q2 * 16, g);
-#pragma unroll
-                    for (int c2 = 0; c2 < 2; ++c2) {
-                        float f[8];
-                        const int n = n_acc + q2 * 16 + c2 * 8;
-                        float bv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                        if (p.bias != nullptr && n < p.N) {
-                            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), v1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32)), g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 36));
-                            bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
-                            bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float a = __uint_as_float(v[c2 * 8 + e]) + bv[e];
-                            const float b = __uint_as_float(g[c2 * 8 + e]) + bg[e];
-                            // the un-fused path rounds the projection to 16 bits before the gating kernel reads it
-                            f[e] = Pack2<T>::round(a) * gelu_erf(Pack2<T>::round(b));
-                        }
-                        const uint4 o = pack8<T>(f);
-                        const uint32_t addr = c_row + (((uint32_t)(cg * 4 + q2 * 2 + c2) ^ sw) << 4);
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-                    }
-                }
-            }
+        };
+        auto post_half = [&](int nt, int mt, int h, bool has_next, int nt2, int mt2, int h2) {
             fence_async_smem();                                          // generic-proxy writes -> visible to the TMA store
             epi_bar();
             if (leader) {
                 const int n0 = nt * BN + h * 128;                        // (a half that starts beyond N holds only zero padding)
                 if (!geglu) {
                     if (n0 < p.N) tma_store_2d(&tm_y, sC, n0, mt * kBM);
-                    if (n0 + 64 < p.N) tma_store_2d(&tm_y, sC + kSlab, n0 + 64, mt * kBM);
+                    if (h * 128 + 64 < BN && n0 + 64 < p.N) tma_store_2d(&tm_y, sC + kSlab, n0 + 64, mt * kBM);
                 } else if (n0 < p.N) {
                     tma_store_2d(&tm_y, sC, n0 >> 1, mt * kBM);
                 }
@@ -408,6 +347,102 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 tma_store_wait_read();                                   // the staging tile may be overwritten
                 if (p.has_res && has_next) load_residual(nt2, mt2, h2);  // lands while the main loop of that tile runs
             }
+        };
+        // 8 accumulator columns (chunk c8 of the thread's 64) -> + bias (+ residual) -> one rounding -> staging tile
+        auto chunk_plain = [&](const uint32_t* v8, int c8, int n_acc) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v8[e]);
+            const int n = n_acc + c8 * 8;
+            if (p.bias != nullptr && n < p.N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            const uint32_t addr = c_row + (((uint32_t)c8 ^ sw) << 4);
+            if (p.has_res) {
+                uint4 rv;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(addr));
+                float r8[8];
+                unpack8<T>(rv, r8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += r8[e];
+            }
+            const uint4 o = pack8<T>(f);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        };
+        // 8 value + 8 gate accumulator columns -> 8 outputs (output chunk `oc` of the thread's 32) -> staging tile
+        auto chunk_geglu = [&](const uint32_t* v8, const uint32_t* g8, int oc, int n_acc) {
+            float f[8];
+            const int n = n_acc + oc * 8;
+            float bv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (p.bias != nullptr && n < p.N) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), v1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 32)), g1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 36));
+                bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
+                bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float a = __uint_as_float(v8[e]) + bv[e];
+                const float b = __uint_as_float(g8[e]) + bg[e];
+                // the un-fused path rounds the projection to 16 bits before the gating kernel reads it
+                f[e] = Pack2<T>::round(a) * gelu_erf(Pack2<T>::round(b));
+            }
+            const uint4 o = pack8<T>(f);
+            const uint32_t addr = c_row + (((uint32_t)(cg * 4 + oc) ^ sw) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        };
+        // Whole-tile style: all 64 columns of the thread in registers at once (two wide TMEM loads in flight, straight-line code)
+        auto emit_half_wide = [&](uint32_t t_col, uint32_t release_bar, int nt, int mt, int h, bool has_next, int nt2, int mt2, int h2) {
+            const int n_acc = nt * BN + h * 128 + cg * 64;
+            const bool mine = h * 128 + cg * 64 < BN;                    // BN = 192: column group 1 has nothing in the second half
+            uint32_t acc[64];
+            if (mine) {
+                tmem_ld32(t_col, acc);
+                tmem_ld32(t_col + 32, acc + 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            if (release_bar) {                                           // accumulator stage fully read: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(release_bar);
+            }
+            pre_half();
+            if (mine) {
+                if (!geglu) {
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) chunk_plain(acc + c8 * 8, c8, n_acc);
+                } else {
+#pragma unroll
+                    for (int oc = 0; oc < 4; ++oc) chunk_geglu(acc + oc * 8, acc + 32 + oc * 8, oc, n_acc);
+                }
+            }
+            post_half(nt, mt, h, has_next, nt2, mt2, h2);
+        };
+        // Split-tile style: the thread's 64 columns arrive 16 at a time through `fetch16(col, v)` (TMEM, or the summed workspace
+        // partials) — few live registers, so the tail path fits beside the rest under the 168-register cap of a 10-warp CTA.
+        auto emit_half = [&](auto&& fetch16, int nt, int mt, int h, bool has_next, int nt2, int mt2, int h2) {
+            const int n_acc = nt * BN + h * 128 + cg * 64;              // first accumulator column of this thread's 64
+            pre_half();
+            if (!geglu) {
+#pragma unroll 1
+                for (int q4 = 0; q4 < 4; ++q4) {                         // 16 columns = two 16-byte chunks
+                    uint32_t v[16];
+                    fetch16(q4 * 16, v);
+                    chunk_plain(v, q4 * 2, n_acc);
+                    chunk_plain(v + 8, q4 * 2 + 1, n_acc);
+                }
+            } else {
+#pragma unroll 1
+                for (int q2 = 0; q2 < 2; ++q2) {                         // 16 value + 16 gate columns -> 16 outputs
+                    uint32_t v[16], g[16];
+                    fetch16(q2 * 16, v);
+                    fetch16(32 + q2 * 16, g);
+                    chunk_geglu(v, g, q2 * 2, n_acc);
+                    chunk_geglu(v + 8, g + 8, q2 * 2 + 1, n_acc);
+                }
+            }
+            post_half(nt, mt, h, has_next, nt2, mt2, h2);
         };
 
         // workspace layout of one (tail tile, slice, half): [epilogue warp][float4 index within the thread's 64 columns][lane],
@@ -429,13 +464,19 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 for (int h = 0; h < C::kHalves; ++h) {
                     const bool last_half = h == C::kHalves - 1;
                     const uint32_t t_col = t_acc + h * 128;
-                    emit_half([&](int col, uint32_t (&v)[16]) { tmem_ld16(t_col + col, v); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); },
-                              nt, mt, h, !last_half || more, last_half ? nx.tile / p.MT : nt, last_half ? nx.tile % p.MT : mt, last_half ? 0 : h + 1);
+                    if constexpr (!SPLIT) {
+                        emit_half_wide(t_col, last_half ? acc_empty + 8 * a : 0u, nt, mt, h, !last_half || more, last_half ? nx.tile / p.MT : nt, last_half ? nx.tile % p.MT : mt, last_half ? 0 : h + 1);
+                    } else {
+                        emit_half([&](int col, uint32_t (&v)[16]) { tmem_ld16(t_col + col, v); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); },
+                                  nt, mt, h, !last_half || more, last_half ? nx.tile / p.MT : nt, last_half ? nx.tile % p.MT : mt, last_half ? 0 : h + 1);
+                    }
                 }
-                tc_fence_before();                                       // accumulator stage fully read: hand it back to the MMA warp
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + 8 * a);
-            } else {
+                if constexpr (SPLIT) {
+                    tc_fence_before();                                   // accumulator stage fully read: hand it back to the MMA warp
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + 8 * a);
+                }
+            } else if constexpr (SPLIT) {
                 // ---- one K-slice of a tail tile: park the partial accumulator in the workspace, then (slices 0 .. halves-1) sum
                 // the S partials of half h = s in slice order and emit it
                 float4* wbase = reinterpret_cast<float4*>(p.ws) + ((size_t)it.tail_idx * p.split + it.s) * (C::kHalves * kHalfF4) + (size_t)ew * 16 * 32 + lane;
@@ -595,41 +636,53 @@ static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
 }
 
 // Split-K plan for `tiles` tiles on `sms` SMs: the r = tiles % sms tiles of the last, partly filled round are cut S ways along
-// K (S <= sms / r, <= kMaxSplit, >= 2 K blocks per slice) when a workspace is available.
-struct Plan { int full_tiles, split, tail_units, grid; double rounds; };
-static Plan make_plan(long long tiles, int KT, int sms, bool can_split) {
+// K (S <= sms / r, <= kMaxSplit, >= kMinSliceK K blocks per slice) when a workspace is available and the K loop is long
+// enough for the workspace round trip to pay (measured, profiles/r02d_kbench_linear.txt: it does at K = 5120, not at 1280).
+constexpr int kMinSplitKT = 40, kMinSliceK = 8;
+struct Plan { int bn, full_tiles, split, tail_units, grid; double cost; };
+static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split) {
     Plan pl;
+    pl.bn = bn;
+    const long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
     const int q = (int)(tiles / sms), r = (int)(tiles % sms);
     int S = 0;
-    if (can_split && r > 0 && g_split_mode != 1) {
+    if (can_split && r > 0 && KT >= kMinSplitKT && bn != 192) {
         S = sms / r;
         if (S > kMaxSplit) S = kMaxSplit;
-        if (S > KT / 2) S = KT / 2;
+        if (S > KT / kMinSliceK) S = KT / kMinSliceK;
         if (S < 2) S = 0;
     }
+    // tensor-pipe rate of a tile width relative to 256 (shared-memory operand bandwidth; 128 measured on ff1, 192 interpolated)
+    const double rate = bn == 256 ? 1.0 : (bn == 192 ? 0.93 : 0.835);
+    double rounds;
     if (S >= 2) {
         pl.full_tiles = q * sms; pl.split = S; pl.tail_units = r * S;
         pl.grid = q > 0 ? sms : pl.tail_units;
-        pl.rounds = q + 1.0 / S + 0.12;                                // + workspace round trip and the finalisers' reads
+        rounds = q + 1.0 / S + 0.25;                                   // + workspace round trip, finalisers' reads, slower epilogue style
     } else {
         pl.full_tiles = (int)tiles; pl.split = 0; pl.tail_units = 0;
         pl.grid = (int)(tiles < sms ? tiles : sms);
-        pl.rounds = q + (r > 0 ? 1.0 : 0.0);
+        rounds = q + (r > 0 ? 1.0 : 0.0);
     }
+    pl.cost = rounds * bn / rate;
     return pl;
 }
 
-// Tile width: fewest (rounds x tile time).  A 128-wide tile re-reads the x tile twice as often and runs the tensor pipe at
-// the shared-memory operand bandwidth — measured 0.835 of the 256-wide rate (profiles/r02b_kbench_linear.txt, ff1) — so it
-// only wins where it saves rounds.
-static int pick_bn(int M, int N, int KT, bool can_split) {
-    if (g_force_bn == 128 || g_force_bn == 256) return g_force_bn;
-    if (N <= 128) return 128;
-    const long long MT = (M + kBM - 1) / kBM;
+// Tile width and split: the plan with the fewest (rounds x tile time).
+static Plan pick_plan(int M, int N, int KT, int epilogue, bool can_split) {
     const int sms = sm_count();
-    const double c128 = make_plan(MT * ((N + 127) / 128), KT, sms, can_split).rounds * 128 / 0.835;
-    const double c256 = make_plan(MT * ((N + 255) / 256), KT, sms, can_split).rounds * 256;
-    return c128 < c256 ? 128 : 256;
+    can_split = can_split && g_split_mode != 1;
+    if (g_force_bn == 128 || g_force_bn == 192 || g_force_bn == 256) return make_plan(M, N, KT, g_force_bn, sms, can_split);
+    Plan best = make_plan(M, N, KT, N <= 128 ? 128 : 256, sms, can_split);
+    if (N > 128) {
+        const Plan p128 = make_plan(M, N, KT, 128, sms, can_split);
+        if (p128.cost < best.cost) best = p128;
+        if (epilogue != TMX_EPI_GEGLU && N > 128) {                    // (a 192-wide GEGLU tile would end in half an output slab)
+            const Plan p192 = make_plan(M, N, KT, 192, sms, can_split);
+            if (p192.cost < best.cost) best = p192;
+        }
+    }
+    return best;
 }
 
 }  // namespace k10
@@ -643,10 +696,11 @@ int linear_init() {
         TMX_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, TMX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
         g_encode = (EncodeTiledFn)fn;
     }
-    TMX_CUDA(cudaFuncSetAttribute(linear_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmem));
-    TMX_CUDA(cudaFuncSetAttribute(linear_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmem));
-    TMX_CUDA(cudaFuncSetAttribute(linear_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmem));
-    TMX_CUDA(cudaFuncSetAttribute(linear_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmem));
+#define K10_KATTR(B16, BN, SP) TMX_CUDA(cudaFuncSetAttribute(linear_kernel<B16, BN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem))
+    K10_KATTR(true, 128, false); K10_KATTR(false, 128, false); K10_KATTR(true, 192, false); K10_KATTR(false, 192, false);
+    K10_KATTR(true, 256, false); K10_KATTR(false, 256, false);
+    K10_KATTR(true, 128, true); K10_KATTR(false, 128, true); K10_KATTR(true, 256, true); K10_KATTR(false, 256, true);
+#undef K10_KATTR
 #define K10_ATTR(T, SR) TMX_CUDA(cudaFuncSetAttribute(lora_t_kernel<T, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
     K10_ATTR(__half, 4); K10_ATTR(__half, 8); K10_ATTR(__half, 12); K10_ATTR(__half, 16);
     K10_ATTR(__nv_bfloat16, 4); K10_ATTR(__nv_bfloat16, 8); K10_ATTR(__nv_bfloat16, 12); K10_ATTR(__nv_bfloat16, 16);
@@ -662,7 +716,7 @@ using namespace tmx::k10;
 extern "C" int tmx_linear_set_variant(int v) {
     // v = tile width (0 auto, 128, 256) + 1000 to disable the split-K tail
     const int bn = v % 1000, nosplit = v / 1000;
-    TMX_REQUIRE(v >= 0 && (bn == 0 || bn == 128 || bn == 256) && nosplit <= 1, TMX_EINVAL, "linear_set_variant: 0 | 128 | 256 (+ 1000 = no split-K tail)");
+    TMX_REQUIRE(v >= 0 && (bn == 0 || bn == 128 || bn == 192 || bn == 256) && nosplit <= 1, TMX_EINVAL, "linear_set_variant: 0 | 128 | 192 | 256 (+ 1000 = no split-K tail)");
     g_force_bn = bn;
     g_split_mode = nosplit;
     return TMX_OK;
@@ -691,14 +745,15 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
     if (int rc = require_init()) return rc;
     const bool bf16 = dtype == TMX_BF16;
     const int KT = K / kBK;
-    const int BN = pick_bn(M, N, KT, workspace != nullptr);
+    Plan pl = pick_plan(M, N, KT, epilogue, workspace != nullptr);
+    if (pl.bn == 192 && epilogue == TMX_EPI_GEGLU) pl = make_plan(M, N, KT, 256, sm_count(), workspace != nullptr && g_split_mode != 1);
+    const int BN = pl.bn;
 
     Params p;
     p.M = M; p.N = N; p.K = K;
     p.MT = (M + kBM - 1) / kBM; p.NT = (N + BN - 1) / BN;
     p.epilogue = epilogue; p.has_res = residual != nullptr; p.bias = bias;
     p.has_tail = 0; p.rows_per_batch = 1; p.tail_mask = 0;
-    const Plan pl = make_plan((long long)p.MT * p.NT, KT, sm_count(), workspace != nullptr);
     p.full_tiles = pl.full_tiles; p.split = pl.split; p.tail_units = pl.tail_units;
     p.sync = reinterpret_cast<unsigned int*>(workspace);
     p.ws = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 4096) : nullptr;
@@ -726,9 +781,14 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
         p.rows_per_batch = lora_rows_per_batch;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const void* fn = BN == 256 ? (bf16 ? (const void*)linear_kernel<true, 256> : (const void*)linear_kernel<false, 256>)
-                               : (bf16 ? (const void*)linear_kernel<true, 128> : (const void*)linear_kernel<false, 128>);
-    const size_t smem = BN == 256 ? Cfg<256>::kSmem : Cfg<128>::kSmem;
+    const bool sp = pl.split >= 2;
+    const void* fn = nullptr;
+#define K10_PICK(BNv, SPv) (bf16 ? (const void*)linear_kernel<true, BNv, SPv> : (const void*)linear_kernel<false, BNv, SPv>)
+    if (BN == 256) fn = sp ? K10_PICK(256, true) : K10_PICK(256, false);
+    else if (BN == 192) fn = K10_PICK(192, false);
+    else fn = sp ? K10_PICK(128, true) : K10_PICK(128, false);
+#undef K10_PICK
+    const size_t smem = BN == 256 ? Cfg<256>::kSmem : (BN == 192 ? Cfg<192>::kSmem : Cfg<128>::kSmem);
     void* args[] = {&mx, &mw, &my, &mr, &mt, &ups, &p};
     if (pl.split >= 2) {
         // the K-slices of a tail tile wait for each other: the grid (<= one CTA per SM) must be co-resident
