@@ -96,7 +96,7 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg=1, out=
 
 def linear_supported(x, w):
     from tweediemix_b200 import ops
-    return ops.GEMM_IMPL == "tmx" and x.shape[-1] % 64 == 0 and w.shape[0] % 8 == 0
+    return ops.GEMM_IMPL != "cublas" and x.shape[-1] % 64 == 0 and w.shape[0] % 8 == 0
 
 
 def linear(x, w, bias=None, *, residual=None, geglu=False, lora_tail=None, out=None):

@@ -151,3 +151,26 @@ def test_second_image_reuses_graphs_with_new_text():
     fresh = b.sample_loop(x0.clone()).cpu()
     assert torch.equal(second, fresh)
     assert not torch.equal(first, second)
+
+
+@pytest.mark.parametrize("impl", ["tmx", "cublas"])
+@pytest.mark.parametrize("lora", [False, True])
+def test_sampler_under_other_gemm_policies(monkeypatch, lora, impl):
+    """The default policy is 'auto' (k10 for the GEGLU and LoRA-tail GEMMs, cuBLAS for the plain projections); 'tmx' (all in
+    k10) and 'cublas' (all in the library) must hold the same parity bound."""
+    _build()
+    from tweediemix_b200 import ops
+    monkeypatch.setattr(ops, "GEMM_IMPL", impl)
+    n, res, dtype = 10, 256, torch.float16
+    ref_unet = synth.make_base_unet(T.RCFG, 1)
+    extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(K)] if lora else \
+            [synth.make_concept_unet(ref_unet, 10 + i) for i in range(K)]
+    orc = T._oracle_sampler(ref_unet, extra, lora, n, res)
+    x0 = orc.initial_latent()
+    want = orc.sample_loop(x0.clone())
+    s = _gpu_sampler(ref_unet, extra, lora, n, res, dtype, True)
+    s.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else s.init_fusion(int(n * 0.2))
+    got = s.sample_loop(x0.clone()).cpu()
+    rel = (got - want).abs().max().item() / want.abs().max().item()
+    print(f"sampler parity lora={lora} fp16 TMX_GEMM={impl}: rel_max={rel:.3e}")
+    assert s.n_forward_rows == orc.n_forward_rows and rel <= TOL_LOOP[dtype]

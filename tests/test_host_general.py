@@ -159,13 +159,15 @@ def test_shared_scheduler_is_not_mutated(monkeypatch):
     assert m1.skip == m2.skip == 200 and m1._alpha_table == m2._alpha_table and len(m2._alpha_table) == 1001
 
 
+@pytest.mark.parametrize("impl", ["cublas", "tmx"])
 @pytest.mark.parametrize("lora", [False, True])
-def test_library_gemm_path_matches_oracle(monkeypatch, lora):
-    """TMX_GEMM=cublas (library GEMM + stand-alone GEGLU / add+LayerNorm / LoRA-delta kernels) is the same function as the
-    default fused-epilogue path: both match the oracle sampler."""
+def test_gemm_policies_match_oracle(monkeypatch, lora, impl):
+    """TMX_GEMM=cublas (library GEMMs + stand-alone GEGLU / add+LayerNorm / LoRA-delta kernels) and TMX_GEMM=tmx (every
+    projection in k10, residual adds in its epilogue) are the same function as the default 'auto' mix (covered by
+    test_host_logic.py): all match the oracle sampler."""
     fake_ops.install(monkeypatch)
     from tweediemix_b200 import ops
-    monkeypatch.setattr(ops, "GEMM_IMPL", "cublas")
+    monkeypatch.setattr(ops, "GEMM_IMPL", impl)
     n, res = 5, 128
     ref_unet = synth.make_base_unet(T.RCFG, 1)
     extra = _extras(ref_unet, T.K, lora)

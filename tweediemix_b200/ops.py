@@ -376,9 +376,23 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg: int = 
 
 # ------------------------------------------------------------------------------------------ k10
 
-# 'tmx' (default): projections / feed-forward GEMMs of the transformer blocks run in the persistent tcgen05 kernel with
-# fused epilogues; 'cublas': library GEMM + separate elementwise kernels (kept for A/B measurements, tools/kbench.py).
-GEMM_IMPL = os.environ.get("TMX_GEMM", "tmx")
+# Which GEMMs of the transformer blocks run in the persistent tcgen05 kernel (k10) and which go to the library:
+#   'auto' (default) — k10 where it is at least as fast as cuBLAS + the stand-alone epilogue kernel on this box
+#                      (profiles/r02e_kbench_linear.txt): the GEGLU projection (value * gelu(gate) in the epilogue: 79.5 vs
+#                      102.9 us at d = 1280, 111 vs 131 us at d = 640) and every projection that carries a LoRA tail (the
+#                      rank-r delta rides as one extra MMA step instead of a separate read-modify-write pass); the plain
+#                      projections, where cuBLAS' tile shapes fill the 148 SMs better (out|q 18.4 vs 21.5 us, ff2 43 vs 52 us),
+#                      stay on cuBLAS with the fused residual-add + LayerNorm kernel behind them;
+#   'tmx'            — every projection / feed-forward GEMM in k10 (residual adds in its epilogue, one-pass LayerNorm after);
+#   'cublas'         — library GEMMs + stand-alone GEGLU / LoRA-delta / add+LayerNorm kernels (A/B measurements).
+GEMM_IMPL = os.environ.get("TMX_GEMM", "auto")
+
+
+def gemm_in_k10(kind: str) -> bool:
+    """Policy: does a GEMM of this kind ('plain', 'geglu', 'lora') run in k10?"""
+    if GEMM_IMPL == "tmx":
+        return True
+    return GEMM_IMPL == "auto" and kind in ("geglu", "lora")
 
 
 _lin_ws = {}
@@ -397,7 +411,7 @@ def _linear_workspace(dev: int) -> torch.Tensor:
 
 def linear_supported(x, w) -> bool:
     """Shapes on the kernel's tile grid (K % 64 == 0, N % 8 == 0, 16-bit CUDA tensors, uniform row stride)."""
-    return (GEMM_IMPL == "tmx" and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and w.dtype == x.dtype
+    return (GEMM_IMPL != "cublas" and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and w.dtype == x.dtype
             and x.shape[-1] % 64 == 0 and w.shape[0] % 8 == 0 and x.is_contiguous() and w.is_contiguous())
 
 

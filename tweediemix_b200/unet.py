@@ -108,10 +108,11 @@ def _f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return hit
 
 
-def _linear(x, weight, bias=None, residual=None, lora_tail=None):
-    """``x @ weight.T + bias (+ residual)``: the persistent tcgen05 GEMM with the bias / residual (/ LoRA tail) in its epilogue
-    when the shape is on its tile grid, else the library GEMM followed by the tmx residual-add kernel."""
-    if ops.linear_supported(x, weight):
+def _linear(x, weight, bias=None, residual=None, lora_tail=None, kind: str = "plain"):
+    """``x @ weight.T + bias (+ residual)``: the persistent tcgen05 GEMM (k10) with the bias / residual (/ LoRA tail) in its
+    epilogue when the policy (``ops.gemm_in_k10``) picks it and the shape is on its tile grid, else the library GEMM followed
+    by the tmx residual-add kernel."""
+    if (lora_tail is not None or ops.gemm_in_k10(kind)) and ops.linear_supported(x, weight):
         return ops.linear(x, weight, _f32(bias), residual=residual, lora_tail=lora_tail)
     assert lora_tail is None
     y = F.linear(x, weight, bias)
@@ -247,16 +248,22 @@ class TmxAttention(nn.Module):
             x = x.to(wdt)
         if encoder_hidden_states is not None and encoder_hidden_states.dtype != wdt:
             encoder_hidden_states = encoder_hidden_states.to(wdt)
+        def tail_of(which, nseg, inp, w):
+            """LoRA deltas of this projection as a fused GEMM tail, when the policy and the shape allow it."""
+            if lora is None or not ops.gemm_in_k10("lora") or not ops.linear_supported(inp, w):
+                return None
+            return lora.tail(which, nseg, inp)
+
         if encoder_hidden_states is None:
             w = self.packed_qkv()
-            tail = lora.tail("qkv", 3, x) if lora is not None and ops.linear_supported(x, w) else None
+            tail = tail_of("qkv", 3, x, w)
             qkv = _linear(x, w, lora_tail=tail)                                   # [B, N, 3*inner]
             if lora is not None and tail is None:
                 lora.add_qkv_self(self, x, qkv)
             q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
         else:
             w = self.to_q.weight
-            tail = lora.tail("q", 1, x) if lora is not None and ops.linear_supported(x, w) else None
+            tail = tail_of("q", 1, x, w)
             q = _linear(x, w, lora_tail=tail)
             if lora is not None and tail is None:
                 lora.add_q(self, x, q)
@@ -264,8 +271,12 @@ class TmxAttention(nn.Module):
             k, v = kv[..., :inner], kv[..., inner:]
         a = ops.attention(q, k, v, self.heads, self.scale)                        # [B, N, inner]
         wo = self.to_out[0].weight
-        tail = lora.tail("out", 1, a) if lora is not None and ops.linear_supported(a, wo) else None
-        o = _linear(a, wo, self.to_out[0].bias, residual=residual, lora_tail=tail)   # bias, residual and LoRA delta in the epilogue
+        tail = tail_of("out", 1, a, wo)
+        # k10: bias, residual and LoRA delta in the epilogue.  Library GEMM: the caller fuses the residual add with the
+        # LayerNorm that follows (``residual_fused`` tells it which happened).
+        fuse = residual is not None and (tail is not None or ops.gemm_in_k10("plain")) and ops.linear_supported(a, wo)
+        self.__dict__["residual_fused"] = fuse
+        o = _linear(a, wo, self.to_out[0].bias, residual=residual if fuse else None, lora_tail=tail)
         if lora is not None and tail is None:
             lora.add_out(self, a, o)
         return o
@@ -334,7 +345,7 @@ class GEGLU(nn.Module):
         return self._il
 
     def forward(self, x):
-        if ops.linear_supported(x, self.proj.weight) and self.proj.weight.shape[0] % 64 == 0:
+        if ops.gemm_in_k10("geglu") and ops.linear_supported(x, self.proj.weight) and self.proj.weight.shape[0] % 64 == 0:
             w, b = self.interleaved()
             return ops.linear(x, w, b, geglu=True)            # value * gelu(gate) in the GEMM epilogue: the [.., 8d] projection never reaches HBM
         return ops.geglu(self.proj(x))
@@ -344,9 +355,14 @@ class FeedForward(nn.Module):
     def __init__(self, dim: int, mult: int = 4):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+        self.residual_fused = False
 
     def forward(self, x, residual=None):
-        return _linear(self.net[0](x), self.net[2].weight, self.net[2].bias, residual=residual)
+        h = self.net[0](x)
+        w = self.net[2].weight
+        fuse = residual is not None and ops.gemm_in_k10("plain") and ops.linear_supported(h, w)
+        self.residual_fused = fuse
+        return _linear(h, w, self.net[2].bias, residual=residual if fuse else None)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -389,21 +405,28 @@ class BasicTransformerBlock(nn.Module):
         g, b = self._p32(norm)
         return ops.residual_add_layer_norm(o, h, g, b, norm.eps, h_out=o)
 
+    def _join(self, o, fused: bool, h, norm: Optional[nn.LayerNorm]):
+        """Residual join after a branch: ``o`` already holds ``branch + h`` when the GEMM epilogue added it (k10) — then only the
+        LayerNorm that follows runs; otherwise the add is fused with that LayerNorm (k6c)."""
+        if fused:
+            return o, (self._ln(norm, o) if norm is not None else None)
+        return self._add_norm(o, h, norm)
+
     def forward(self, h, encoder_hidden_states, n=None, next_norm: Optional[nn.LayerNorm] = None):
-        """``n`` = norm1(h) if the caller already has it; returns (h_out, next_norm(h_out) or None).
-        Fused path (k10): every residual add rides in the epilogue of the GEMM that produces the branch output, the
-        LayerNorm that follows is the stand-alone one-pass kernel.  Library-GEMM path: the add is fused with that
-        LayerNorm instead (k6c)."""
+        """``n`` = norm1(h) if the caller already has it; returns (h_out, next_norm(h_out) or None)."""
         if n is None:
             n = self._ln(self.norm1, h)
-        if ops.linear_supported(n, self.attn1.to_q.weight):
-            h = self._call_attn(self.attn1, n, None, residual=h)
-            h = self._call_attn(self.attn2, self._ln(self.norm2, h), encoder_hidden_states, residual=h)
-            h = self.ff(self._ln(self.norm3, h), residual=h)
-            return h, (self._ln(next_norm, h) if next_norm is not None else None)
-        h, n = self._add_norm(self._call_attn(self.attn1, n, None), h, self.norm2)
-        h, n = self._add_norm(self._call_attn(self.attn2, n, encoder_hidden_states), h, self.norm3)
-        return self._add_norm(self.ff(n), h, next_norm)
+        o = self._call_attn(self.attn1, n, None, residual=h)
+        h, n = self._join(o, self._fused(self.attn1), h, self.norm2)
+        o = self._call_attn(self.attn2, n, encoder_hidden_states, residual=h)
+        h, n = self._join(o, self._fused(self.attn2), h, self.norm3)
+        o = self.ff(n, residual=h)
+        return self._join(o, self.ff.residual_fused, h, next_norm)
+
+    @staticmethod
+    def _fused(attn) -> bool:
+        core = attn.__dict__.get("_tmx_view", attn)
+        return bool(core.__dict__.get("residual_fused", False))
 
 
 class Transformer2DModel(nn.Module):
@@ -424,7 +447,7 @@ class Transformer2DModel(nn.Module):
         blocks = self.transformer_blocks
         for i, blk in enumerate(blocks):
             h, n = blk(h, encoder_hidden_states, n, blocks[i + 1].norm1 if i + 1 < len(blocks) else None)
-        return _image(_linear(h, self.proj_out.weight, self.proj_out.bias, residual=_tokens(x)), hh, ww)   # + x in the epilogue
+        return _image(_linear(h, self.proj_out.weight, self.proj_out.bias, residual=_tokens(x)), hh, ww)   # + x (k10 epilogue / k6)
 
 
 # =============================================================================== ResNet / sampling blocks
