@@ -311,8 +311,8 @@ template <int HV> struct AttnCfg {
 };
 constexpr int kTmemCols = 512;
 constexpr int kBars = 6 * kSlots + 2 * kQBufs * kSlots + 4 * kStages;
-constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages) * kTileBytes + kBars * 8 + 16 + 2 * kSlots * 2 * kBM * 4 /*l_xchg*/
-                           + 2 * kSlots * 2 * kBM * 4 /*m_xchg (HV == 2 with -DTMX_ATTN_HV2_XCHG)*/;
+constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages + kSlots /*O staging*/) * kTileBytes + kBars * 8 + 16
+                           + 2 * kSlots * 2 * kBM * 4 /*l_xchg*/ + 2 * kSlots * 2 * kBM * 4 /*m_xchg (HV == 2 with -DTMX_ATTN_HV2_XCHG)*/;
 
 // One scheduling step of a CTA: query tile `qt` (and qt+1 when nslots == 2) of head h, batch b.
 struct Step { int b, h, qt, nslots; };
@@ -332,7 +332,7 @@ __device__ __forceinline__ bool next_step(int& it, int end, int QT, int H, int p
 template <bool BF16, int HV>
 __global__ void __launch_bounds__(AttnCfg<HV>::kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, void* __restrict__ o_ptr, long long o_stride_n,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                 int Nq, int Nk, int H, int QT, int total_tiles, int pair, float scale_log2) {
     using Cfg = AttnCfg<HV>;
     constexpr int ST = kStages;
@@ -342,11 +342,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t* sQ = smem;                                   // [kQBufs][kSlots] tiles
     uint8_t* sK = sQ + kQBufs * kSlots * kTileBytes;      // [ST]
     uint8_t* sV = sK + ST * kTileBytes;                   // [ST]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * kTileBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + (ST + kSlots) * kTileBytes);
     uint32_t sQ_a = smem_u32(sQ);
     asm volatile("mov.u32 %0, %0;" : "+r"(sQ_a));         // opaque: keep it in a register instead of re-deriving it (S2UR chain) at every use
     const uint32_t sK_a = sQ_a + kQBufs * kSlots * kTileBytes, sV_a = sK_a + ST * kTileBytes;
-    const uint32_t q_full = sV_a + ST * kTileBytes;       // [kQBufs*kSlots]  TMA -> MMA : Q tile landed
+    const uint32_t sO_a = sV_a + ST * kTileBytes;         // [kSlots] output staging tiles (128 rows x 128 B, SWIZZLE_128B) for the TMA store
+    const uint32_t q_full = sO_a + kSlots * kTileBytes;   // [kQBufs*kSlots]  TMA -> MMA : Q tile landed
     const uint32_t q_empty = q_full + 8 * kQBufs * kSlots; // [kQBufs*kSlots]  MMA -> TMA : last S = Q K^T of the step issued
     const uint32_t s_full = q_empty + 8 * kQBufs * kSlots; // [kSlots]  MMA -> softmax   : S(n) complete
     const uint32_t s_free = s_full + 8 * kSlots;           // [kSlots]  softmax -> MMA   : S(n) copied to registers
@@ -375,7 +376,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == kUtilWarp) {
-        if (lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
+        if (lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o); }
         __syncwarp();
         tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     }
@@ -711,28 +712,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float inv_l = 1.f / l_sum;
             mbar_wait(bar_pv_done, (n - 1u) & 1u);
             tc_fence_after();
-            const int q_row = (cur.qt + w) * kBM + row;
-            uint8_t* dst = reinterpret_cast<uint8_t*>(o_ptr) +
-                           (((size_t)cur.b * Nq + (size_t)q_row) * (size_t)o_stride_n + (size_t)cur.h * kD + half * OC) * 2;
+            // O / l -> 16-bit -> this slot's staging tile (row r = 128 B, 16-byte chunks XOR-swizzled with r & 7) -> ONE TMA store of
+            // the 128 x 64 tile: full-line bulk writes instead of 32 scattered 16-byte stores per warp instruction, rows beyond Nq
+            // clipped by the tensor map.  Barrier A: the issuing thread has seen its previous store read the tile; barrier B: all rows written.
+            const uint32_t o_row = sO_a + w * kTileBytes + row * 128;
+            const uint32_t o_sw = (uint32_t)(row & 7);
+            asm volatile("bar.sync %0, %1;" :: "r"(11 + w), "n"(128 * HV) : "memory");
 #pragma unroll
             for (int g = 0; g < OC / 32; ++g) {
                 uint32_t o[32];
                 tmem_ld32(t_row + 128 + half * OC + g * 32, o);
                 tc_wait_ld();
-                if (q_row < Nq) {
 #pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        uint4 v;
-                        v.x = pack2<BF16>(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-                        v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-                        v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-                        v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-                        *reinterpret_cast<uint4*>(dst + (g * 32 + c) * 2) = v;
-                    }
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 v;
+                    v.x = pack2<BF16>(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+                    v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+                    v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+                    v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+                    const uint32_t chunk = (uint32_t)((half * OC + g * 32 + c) >> 3);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(o_row + ((chunk ^ o_sw) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                 }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" :: "r"(13 + w), "n"(128 * HV) : "memory");
+            if (half == 0 && quarter == 0 && lane == 0) {
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             :: "l"(reinterpret_cast<uint64_t>(&tm_o)), "r"(sO_a + w * kTileBytes), "r"(0), "r"(cur.h), "r"((cur.qt + w) * kBM), "r"(cur.b) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
             tc_fence_before();           // order the O reads before the next step's P(0) hand-off (p_full arrive)
         }
+        if (half == 0 && quarter == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -823,7 +835,8 @@ extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (int rc = require_init()) return rc;
 
     const bool bf16 = dtype == TMX_BF16;
-    CUtensorMap mq, mk, mv;
+    CUtensorMap mq, mk, mv, mo;
+    if (int rc = make_map(&mo, o, B, Nq, H, o_stride_n, bf16)) return rc;
     if (int rc = make_map(&mq, q, B, Nq, H, q_stride_n, bf16)) return rc;
     if (int rc = make_map(&mk, k, B, Nk, H, k_stride_n, bf16)) return rc;
     if (int rc = make_map(&mv, v, B, Nk, H, v_stride_n, bf16)) return rc;
@@ -833,7 +846,7 @@ extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o
     // persistent grid: one CTA per SM, never more CTAs than (pairs of) query tiles
     const long long units = pair ? (total + 1) / 2 : total;
     const int grid = (int)(units < sm_count() ? units : sm_count());
-#define TMX_ATTN_LAUNCH(B16, HV) attn_fwd_kernel<B16, HV><<<grid, AttnCfg<HV>::kThreads, kSmemBytes, st>>>(mq, mk, mv, o, o_stride_n, Nq, Nk, H, QT, (int)total, pair, scale_log2)
+#define TMX_ATTN_LAUNCH(B16, HV) attn_fwd_kernel<B16, HV><<<grid, AttnCfg<HV>::kThreads, kSmemBytes, st>>>(mq, mk, mv, mo, Nq, Nk, H, QT, (int)total, pair, scale_log2)
     if (g_halves == 2) { if (bf16) TMX_ATTN_LAUNCH(true, 2); else TMX_ATTN_LAUNCH(false, 2); }
     else               { if (bf16) TMX_ATTN_LAUNCH(true, 1); else TMX_ATTN_LAUNCH(false, 1); }
 #undef TMX_ATTN_LAUNCH
