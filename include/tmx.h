@@ -250,6 +250,26 @@ TMX_API int tmx_linear_set_variant(int v);
 TMX_API int tmx_lora_t_fwd(const void* x, const void* const* lora_down, void* t, int B, int M, int K, int64_t ldx,
                    int sr, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * k11 — video loop (I2VGen-XL stage): classifier-free guidance + v-prediction Tweedie estimate + DDIM update, one pass
+ * over the flat latents (position-wise, so the reference's [B,C,F,H,W] <-> [(B F),C,H,W] permutes are not needed):
+ *   v = v_u + g (v_c - v_u);  eps = sqrt(a_t) v + sqrt(1-a_t) x;  x0 = sqrt(a_t) x - sqrt(1-a_t) v;
+ *   x_next = sqrt(a_next) x0 + sqrt(1-a_next) eps
+ * Replaces video_gen/pipeline_i2vgen_xl.py:694-713.  x, v_uncond, v_cond, x_next (, x0_out or NULL): dtype [n], n % 8 == 0;
+ * dtype TMX_F16 / TMX_BF16 / TMX_F32; round_mode as for the blend kernels (TMX_ROUND_REF = the fp16 pipeline's roundings).
+ * Algorithmic bytes: (4 or 5) * n * sizeof(dtype).
+ */
+TMX_API int tmx_vpred_cfg_ddim_fwd(const void* x, const void* v_uncond, const void* v_cond, void* x_next, void* x0_out,
+                           size_t n, float a_t, float a_next, float guidance, int dtype, int round_mode, void* stream);
+
+/* k12 — frame-0 residual-feature injection, in place, on a ResNet output viewed as [groups, frames, frame_elems]
+ * (the reference hard-codes groups = 2, frames = 16): y[g, t >= 1] = interp * y[g, 0] + (1 - interp) * y[g, t];
+ * interp = 1 copies frame 0 (`injection_schedule`, video_gen/utils_attn.py:433-443), 0 < interp < 1 is the
+ * `injection_schedule2` blend (:445-456).  frame_elems % 8 == 0; dtype TMX_F16 / TMX_BF16.
+ */
+TMX_API int tmx_frame_inject_fwd(void* y, int groups, int frames, size_t frame_elems, float interp, int dtype, int round_mode,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ SIGNATURES = {
     "tmx_linear_workspace_bytes": (_sz, []),
     "tmx_linear_set_variant": (_i, [_i]),
     "tmx_lora_t_fwd": (_i, [_vp, C.POINTER(_vp), _vp, _i, _i, _i, _i64, _i, _i, _vp]),
+    "tmx_vpred_cfg_ddim_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _i, _i, _vp]),
+    "tmx_frame_inject_fwd": (_i, [_vp, _i, _i, _sz, _f, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

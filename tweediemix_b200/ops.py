@@ -485,6 +485,41 @@ def lora_t(x, downs, sr: int):
     return t
 
 
+# ------------------------------------------------------------------------------------------ k11 / k12 (video loop)
+
+def vpred_cfg_ddim(x, v_uncond, v_cond, a_t: float, a_next: float, g: float, *, out=None, x0_out=None, ref_rounding=False):
+    """CFG + v-prediction Tweedie x0 + DDIM update of the video latents (video_gen/pipeline_i2vgen_xl.py:694-713); any shape,
+    all tensors contiguous and of one dtype (fp16 / bf16 / fp32).  Returns x_next."""
+    _dev(x, v_uncond, v_cond, out, x0_out)
+    assert x.is_contiguous() and v_uncond.is_contiguous() and v_cond.is_contiguous()
+    assert x.dtype == v_uncond.dtype == v_cond.dtype and x.shape == v_uncond.shape == v_cond.shape
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.dtype == x.dtype and (x0_out is None or (x0_out.is_contiguous() and x0_out.dtype == x.dtype))
+    n = x.numel()
+    with _Launch("vpred", 1, f"n{n}", (4 + (1 if x0_out is not None else 0)) * n * x.element_size()):
+        rc = _lib.load().tmx_vpred_cfg_ddim_fwd(_p(x), _p(v_uncond), _p(v_cond), _p(out), _p(x0_out), n, float(a_t), float(a_next), float(g),
+                                                _dt(x), _lib.ROUND_REF if ref_rounding else _lib.ROUND_FP32, _stream())
+    _lib.check(rc, "tmx_vpred_cfg_ddim_fwd")
+    return out
+
+
+def frame_inject(y, groups: int, frames: int, interp: float = 1.0, *, ref_rounding=False):
+    """In place on a dense [(groups frames), ...] 16-bit tensor: frames 1.. of every group become
+    interp * frame 0 + (1 - interp) * themselves (video_gen/utils_attn.py:433-456)."""
+    _dev(y)
+    if y.shape[0] != groups * frames:
+        raise RuntimeError(f"tmx.frame_inject: leading dim {y.shape[0]} is not groups x frames = {groups} x {frames}")
+    dense = y.is_contiguous() or (y.dim() == 4 and y.is_contiguous(memory_format=torch.channels_last))
+    if not dense:
+        raise RuntimeError("tmx.frame_inject: y must be dense (contiguous or channels_last)")
+    with _Launch("frame_inject", 1, "", 2.0 * y.numel() * y.element_size()):
+        rc = _lib.load().tmx_frame_inject_fwd(_p(y), int(groups), int(frames), y.numel() // (groups * frames), float(interp), _dt(y),
+                                              _lib.ROUND_REF if ref_rounding else _lib.ROUND_FP32, _stream())
+    _lib.check(rc, "tmx_frame_inject_fwd")
+    return y
+
+
 # ------------------------------------------------------------------------------------------ k1/k2
 
 def attention(q, k, v, heads: int, scale: float | None = None, out=None):
