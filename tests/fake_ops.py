@@ -132,6 +132,28 @@ def lora_t(x, downs, sr):
     return t
 
 
+def vpred_cfg_ddim(x, v_uncond, v_cond, a_t, a_next, g, *, out=None, x0_out=None, ref_rounding=False):
+    xf, u, c = x.float(), v_uncond.float(), v_cond.float()
+    v = u + g * (c - u)
+    sa, sb, sna, snb = a_t ** 0.5, (1 - a_t) ** 0.5, a_next ** 0.5, (1 - a_next) ** 0.5
+    eps = sa * v + sb * xf
+    x0 = sa * xf - sb * v
+    res = (sna * x0 + snb * eps).to(x.dtype)
+    if x0_out is not None:
+        x0_out.copy_(x0.to(x.dtype))
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def frame_inject(y, groups, frames, interp=1.0, *, ref_rounding=False):
+    v = y.reshape(groups, frames, -1)
+    first = v[:, :1].float()
+    v[:, 1:] = (interp * first + (1.0 - interp) * v[:, 1:].float()).to(y.dtype) if interp != 1.0 else v[:, :1].expand_as(v[:, 1:])
+    return y
+
+
 def _mw(masks, weights, K, like):
     m = masks if masks is not None else torch.ones(K, 1, 1, 1, device=like.device)
     if weights is not None:
@@ -181,7 +203,8 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
 
 
 NAMES = ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention",
-         "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear", "linear", "lora_t", "linear_supported")
+         "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear", "linear", "lora_t", "linear_supported",
+         "vpred_cfg_ddim", "frame_inject")
 
 
 def install(monkeypatch):

@@ -168,6 +168,17 @@ def main():
             us = timeit(lambda i: ops.tweedie_blend_ddim(x, e, m, 0.0438, 0.0518, 0.8, out=o), 1, args.reps)
             nbytes = imgs * (4 * 16384 * 8 + 16 * 16384 * 2) + 3 * 16384 * 4
             out.append(("blend", f"imgs{imgs}", us, nbytes / us / 1e3, "GB/s", hbm))
+    if want("video"):
+        # k11 / k12 of the I2VGen-XL stage: one 1280x720 16-frame video (4 x 16 x 90 x 160 latents) and a stack of 64 of them
+        for vids in (1, 64):
+            n = vids * 4 * 16 * 90 * 160
+            x, vu, vc, o = (torch.randn(n, device=dev, dtype=DT) for _ in range(4))
+            us = timeit(lambda i: ops.vpred_cfg_ddim(x, vu, vc, 0.5, 0.6, 9.0, out=o), 1, args.reps)
+            out.append(("video", f"vpred_videos{vids}", us, 4 * n * 2 / us / 1e3, "GB/s", hbm))
+        for C, hw in [(1280, 23 * 40), (1280, 45 * 80)]:                          # mid block / up block 1 feature maps of a 720p run
+            y = torch.randn(32, C, hw, device=dev, dtype=DT)
+            us = timeit(lambda i: ops.frame_inject(y, 2, 16, 0.7), 1, args.reps)
+            out.append(("video", f"inject_C{C}_HW{hw}", us, 2 * 30 * C * hw * 2 / us / 1e3, "GB/s", hbm))
     if want("routed"):
         # k3: grouped tcgen05 GEMM (custom cross K/V, text-only: once per prompt set) and the rank-4 LoRA delta kernel
         for d, H in [(1280, 20), (640, 10)]:

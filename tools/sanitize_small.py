@@ -83,6 +83,11 @@ def main():
             for s_ in range(2):
                 want[b, :, s_ * 72:(s_ + 1) * 72] += t[:, s_ * 4:(s_ + 1) * 4] @ up[b][s_ * 72:(s_ + 1) * 72].float().t()
         assert (yl.float() - want).abs().max() < 6e-2
+    # k11 / k12: video step and frame-0 injection
+    lat, vv = rnd(1, 4, 16, 3, 4).to(bf), rnd(2, 4, 16, 3, 4).to(bf)
+    ops.vpred_cfg_ddim(lat, vv[:1].contiguous(), vv[1:].contiguous(), 0.3, 0.4, 9.0, x0_out=torch.empty_like(lat), ref_rounding=True)
+    ops.frame_inject(rnd(32, 8, 3, 3).to(bf), 2, 16, 0.7)
+    ops.frame_inject(rnd(32, 8, 3, 3).to(bf), 2, 16, 1.0, ref_rounding=True)
     xs_, ws_ = rnd(256, 2560).to(bf), (rnd(256, 2560) / 50).to(bf)          # 2 tiles, K = 2560: split-K tail (cooperative launch)
     _lib.load().tmx_linear_set_variant(0)
     ys_ = ops.linear(xs_, ws_, rnd(256), residual=rnd(256, 256).to(bf))
