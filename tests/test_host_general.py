@@ -28,7 +28,7 @@ def _extras(ref_unet, k, lora):
 @pytest.mark.parametrize("k,lora", [(8, False), (2, True)])
 def test_sampler_other_concept_counts_match_oracle(monkeypatch, k, lora):
     fake_ops.install(monkeypatch)
-    n, res = 5, 128
+    n, res = 5, 64
     ref_unet = synth.make_base_unet(T.RCFG, 1)
     extra = _extras(ref_unet, k, lora)
     prod = T._product_sampler(ref_unet, extra, lora, n, res, k=k)
@@ -168,7 +168,7 @@ def test_gemm_policies_match_oracle(monkeypatch, lora, impl):
     fake_ops.install(monkeypatch)
     from tweediemix_b200 import ops
     monkeypatch.setattr(ops, "GEMM_IMPL", impl)
-    n, res = 5, 128
+    n, res = 5, 64
     ref_unet = synth.make_base_unet(T.RCFG, 1)
     extra = _extras(ref_unet, T.K, lora)
     prod = T._product_sampler(ref_unet, extra, lora, n, res)
