@@ -620,7 +620,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_force_bn = 0;     // tuning hook: 0 = heuristic, 128 / 256 = forced tile width
-static int g_split_mode = 0;   // tuning hook: 0 = split-K tail when a workspace is given, 1 = never
+static int g_split_mode = 0;   // tuning hook: 0 = split-K tail when a workspace is given and K is long, 1 = never, 2 = at any K
 
 // 2-D map over a row-major [rows, cols] 16-bit matrix with row stride ld (elements): dims (cols, rows), box (64, box_rows)
 static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows, bool bf16) {
@@ -646,10 +646,12 @@ static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split) {
     const long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
     const int q = (int)(tiles / sms), r = (int)(tiles % sms);
     int S = 0;
-    if (can_split && r > 0 && KT >= kMinSplitKT && bn != 192) {
+    const bool eager = g_split_mode == 2;                              // tuning hook: split whenever a slice keeps >= 4 K blocks
+    if (can_split && r > 0 && (KT >= kMinSplitKT || eager) && bn != 192) {
         S = sms / r;
         if (S > kMaxSplit) S = kMaxSplit;
-        if (S > KT / kMinSliceK) S = KT / kMinSliceK;
+        const int min_slice = eager ? 4 : kMinSliceK;
+        if (S > KT / min_slice) S = KT / min_slice;
         if (S < 2) S = 0;
     }
     // tensor-pipe rate of a tile width relative to 256 (shared-memory operand bandwidth; 128 measured on ff1, 192 interpolated)
@@ -716,7 +718,8 @@ using namespace tmx::k10;
 extern "C" int tmx_linear_set_variant(int v) {
     // v = tile width (0 auto, 128, 256) + 1000 to disable the split-K tail
     const int bn = v % 1000, nosplit = v / 1000;
-    TMX_REQUIRE(v >= 0 && (bn == 0 || bn == 128 || bn == 192 || bn == 256) && nosplit <= 1, TMX_EINVAL, "linear_set_variant: 0 | 128 | 192 | 256 (+ 1000 = no split-K tail)");
+    TMX_REQUIRE(v >= 0 && (bn == 0 || bn == 128 || bn == 192 || bn == 256) && nosplit <= 2, TMX_EINVAL,
+                "linear_set_variant: 0 | 128 | 192 | 256 (+ 1000 = no split-K tail, + 2000 = split-K tail at any K)");
     g_force_bn = bn;
     g_split_mode = nosplit;
     return TMX_OK;
