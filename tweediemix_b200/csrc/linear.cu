@@ -640,7 +640,7 @@ static int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t ro
 // enough for the workspace round trip to pay (measured, profiles/r02d_kbench_linear.txt: it does at K = 5120, not at 1280).
 constexpr int kMinSplitKT = 40, kMinSliceK = 8;
 struct Plan { int bn, full_tiles, split, tail_units, grid; double cost; };
-static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split) {
+static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split, int epilogue = TMX_EPI_NONE, bool has_res = false) {
     Plan pl;
     pl.bn = bn;
     const long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
@@ -654,34 +654,39 @@ static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split) {
         if (S > KT / min_slice) S = KT / min_slice;
         if (S < 2) S = 0;
     }
-    // tensor-pipe rate of a tile width relative to 256 (shared-memory operand bandwidth; 128 measured on ff1, 192 interpolated)
-    const double rate = bn == 256 ? 1.0 : (bn == 192 ? 0.93 : 0.835);
+    // Cost model fitted to profiles/r02j_kbench_linear.txt.  A tile takes the longer of its main loop — KT K-blocks of four
+    // MMAs at bn/2 clk each, slowed by the shared-memory operand bandwidth for narrower tiles (0.78 / 0.93 of the 256-wide rate) —
+    // and its epilogue (~4000 clk per 128 columns, more with a residual or the GEGLU gating), which bounds the K = 640 shapes.
+    const double rate = bn == 256 ? 1.0 : (bn == 192 ? 0.93 : 0.78);
+    const double main_clk = KT * 2.0 * bn / rate;
+    const double epi_clk = bn / 128.0 * (4000.0 + (has_res ? 1000.0 : 0.0) + (epilogue == TMX_EPI_GEGLU ? 2000.0 : 0.0));
+    const double tile_clk = main_clk > epi_clk ? main_clk : epi_clk;
     double rounds;
     if (S >= 2) {
         pl.full_tiles = q * sms; pl.split = S; pl.tail_units = r * S;
         pl.grid = q > 0 ? sms : pl.tail_units;
-        rounds = q + 1.0 / S + 0.25;                                   // + workspace round trip, finalisers' reads, slower epilogue style
+        rounds = q + 1.0 / S + (bn == 256 ? 0.25 : 0.5);               // + workspace round trip, finalisers' reads (one finaliser per 128-wide tile), slower epilogue style
     } else {
         pl.full_tiles = (int)tiles; pl.split = 0; pl.tail_units = 0;
         pl.grid = (int)(tiles < sms ? tiles : sms);
         rounds = q + (r > 0 ? 1.0 : 0.0);
     }
-    pl.cost = rounds * bn / rate;
+    pl.cost = rounds * tile_clk;
     return pl;
 }
 
 // Tile width and split: the plan with the fewest (rounds x tile time).
-static Plan pick_plan(int M, int N, int KT, int epilogue, bool can_split) {
+static Plan pick_plan(int M, int N, int KT, int epilogue, bool has_res, bool can_split) {
     const int sms = sm_count();
     can_split = can_split && g_split_mode != 1;
-    if (g_force_bn == 128 || g_force_bn == 192 || g_force_bn == 256) return make_plan(M, N, KT, g_force_bn, sms, can_split);
-    Plan best = make_plan(M, N, KT, N <= 128 ? 128 : 256, sms, can_split);
+    if (g_force_bn == 128 || g_force_bn == 192 || g_force_bn == 256) return make_plan(M, N, KT, g_force_bn, sms, can_split, epilogue, has_res);
+    Plan best = make_plan(M, N, KT, N <= 128 ? 128 : 256, sms, can_split, epilogue, has_res);
     if (N > 128) {
-        const Plan p128 = make_plan(M, N, KT, 128, sms, can_split);
+        const Plan p128 = make_plan(M, N, KT, 128, sms, can_split, epilogue, has_res);
         if (p128.cost < best.cost) best = p128;
-        if (epilogue != TMX_EPI_GEGLU && N > 128) {                    // (a 192-wide GEGLU tile would end in half an output slab)
-            const Plan p192 = make_plan(M, N, KT, 192, sms, can_split);
-            if (p192.cost < best.cost) best = p192;
+        if (epilogue != TMX_EPI_GEGLU) {                               // (a 192-wide GEGLU tile would end in half an output slab)
+            const Plan p192 = make_plan(M, N, KT, 192, sms, can_split, epilogue, has_res);
+            if (p192.cost < best.cost * 0.97) best = p192;
         }
     }
     return best;
@@ -748,8 +753,8 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
     if (int rc = require_init()) return rc;
     const bool bf16 = dtype == TMX_BF16;
     const int KT = K / kBK;
-    Plan pl = pick_plan(M, N, KT, epilogue, workspace != nullptr);
-    if (pl.bn == 192 && epilogue == TMX_EPI_GEGLU) pl = make_plan(M, N, KT, 256, sm_count(), workspace != nullptr && g_split_mode != 1);
+    Plan pl = pick_plan(M, N, KT, epilogue, residual != nullptr, workspace != nullptr);
+    if (pl.bn == 192 && epilogue == TMX_EPI_GEGLU) pl = make_plan(M, N, KT, 256, sm_count(), workspace != nullptr && g_split_mode != 1, epilogue, false);
     const int BN = pl.bn;
 
     Params p;

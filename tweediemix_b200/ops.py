@@ -378,7 +378,7 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg: int = 
 
 # Which GEMMs of the transformer blocks run in the persistent tcgen05 kernel (k10) and which go to the library:
 #   'auto' (default) — k10 where it is at least as fast as cuBLAS + the stand-alone epilogue kernel on this box
-#                      (profiles/r02e_kbench_linear.txt): the GEGLU projection (value * gelu(gate) in the epilogue: 79.5 vs
+#                      (profiles/r02j_kbench_linear.txt): the GEGLU projection (value * gelu(gate) in the epilogue: 79.5 vs
 #                      102.9 us at d = 1280, 111 vs 131 us at d = 640) and every projection that carries a LoRA tail (the
 #                      rank-r delta rides as one extra MMA step instead of a separate read-modify-write pass); the plain
 #                      projections, where cuBLAS' tile shapes fill the 148 SMs better (out|q 18.4 vs 21.5 us, ff2 43 vs 52 us),
