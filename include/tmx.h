@@ -135,6 +135,12 @@ TMX_API int    tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
 /* Tuning / test hook: 0 = fused single-launch path when applicable (default), 1 = always two launches,
  * 2 = fused kernel through a plain (non-cooperative) launch. */
 TMX_API int tmx_groupnorm_set_variant(int v);
+
+/* Same as tmx_groupnorm_fwd (NHWC, 16-bit) over the channel concatenation [x1 | x2] WITHOUT materialising it: x1 is
+ * [N, HW, C1], x2 is [N, HW, C - C1] (C1 % 8 == 0), y is [N, HW, C].  Replaces the torch.cat([hidden, skip], dim=1) that feeds
+ * norm1 of every up-block ResnetBlock2D ([D] unet_2d_blocks.py) — 9 copies of up to 126 MB per U-Net forward. */
+TMX_API int tmx_groupnorm_cat_fwd(const void* x1, const void* x2, int C1, const float* gamma, const float* beta, const float* add,
+                          void* y, void* workspace, int N, int C, int HW, int G, float eps, int act, int dtype, void* stream);
 /* Number of kernels tmx_groupnorm_fwd launches for this shape (1 fused, 2 stats + apply): launch accounting. */
 TMX_API int tmx_groupnorm_launches(int N, int C, int HW, int layout, int dtype);
 

@@ -10,7 +10,9 @@ import torch.nn.functional as F
 from oracle import step_math as sm
 
 
-def group_norm(x, gamma, beta, groups, eps, *, silu=False, add=None, out=None):
+def group_norm(x, gamma, beta, groups, eps, *, silu=False, add=None, out=None, x2=None):
+    if x2 is not None:
+        x = torch.cat([x, x2], dim=1)
     xf = x.float()
     if add is not None:
         xf = xf + add[:, :, None, None]
@@ -92,6 +94,10 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg=1, out=
                 up = lora_up[b][s_ * seg:(s_ + 1) * seg].float()              # [seg, r]
                 out[b, :, s_ * seg:(s_ + 1) * seg] += (t[:, s_ * r:(s_ + 1) * r] @ up.t()).to(out.dtype)
     return out
+
+
+def cat_free_supported(a, b):
+    return a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0
 
 
 def linear_supported(x, w):
@@ -204,7 +210,7 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
 
 NAMES = ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention",
          "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear", "linear", "lora_t", "linear_supported",
-         "vpred_cfg_ddim", "frame_inject")
+         "vpred_cfg_ddim", "frame_inject", "cat_free_supported")
 
 
 def install(monkeypatch):

@@ -185,6 +185,32 @@ def test_groupnorm_matches_fp32_reference(dtype, layout, shape, gn_variant):
                                        rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(4, 1280, 1280, 32, 32), (4, 1280, 640, 32, 32), (4, 640, 320, 64, 64), (2, 640, 320, 128, 128),
+                                   (4, 320, 320, 128, 128), (2, 64, 128, 9, 7), (1, 8, 56, 3, 3)])   # N, C1, C2, H, W: the SDXL up-block sites + ragged
+def test_groupnorm_two_sources_equals_cat(dtype, shape, gn_variant):
+    """group_norm(a, x2=b) == group_norm(cat([a, b], 1)): the up-block ResNets read (hidden, skip) without the torch.cat copy; groups may
+    straddle the source boundary (1280 + 640 channels: 60 per group)."""
+    o = ops()
+    N, C1, C2, H, W = shape
+    C = C1 + C2
+    g = torch.Generator().manual_seed(C + H)
+    a = (torch.randn(N, C1, H, W, generator=g) * 1.3 + 0.4).to(dtype)
+    b = (torch.randn(N, C2, H, W, generator=g) * 0.7 - 0.2).to(dtype)
+    gamma, beta = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    add = 0.5 * torch.randn(N, C, generator=g)
+    ac, bc = (t.cuda().contiguous(memory_format=torch.channels_last) for t in (a, b))
+    for silu, use_add in [(True, False), (True, True), (False, False)]:
+        want = _gn_ref(torch.cat([a, b], 1), gamma, beta, 32 if C % 32 == 0 else 8, 1e-5, add if use_add else None, silu)
+        got = o.group_norm(ac, gamma.cuda(), beta.cuda(), 32 if C % 32 == 0 else 8, 1e-5, silu=silu, add=add.cuda() if use_add else None, x2=bc)
+        assert got.shape == (N, C, H, W) and got.is_contiguous(memory_format=torch.channels_last)
+        torch.testing.assert_close(got.cpu().float(), want.to(dtype).float(), rtol=2 ** -7 if dtype == torch.bfloat16 else 2 ** -10, atol=2e-3)
+        # and bit-identical to the single-source kernel on the materialised concatenation (same arithmetic, same order)
+        cat = torch.cat([a, b], 1).cuda().contiguous(memory_format=torch.channels_last)
+        one = o.group_norm(cat, gamma.cuda(), beta.cuda(), 32 if C % 32 == 0 else 8, 1e-5, silu=silu, add=add.cuda() if use_add else None)
+        assert torch.equal(got, one)
+
+
 def test_groupnorm_large_mean_is_stable_and_inplace(gn_variant):
     """|mean| >> std: the pivot-shifted sums must not cancel catastrophically."""
     o = ops()

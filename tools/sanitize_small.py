@@ -33,6 +33,14 @@ def main():
         y = ops.group_norm(x, torch.ones(shape[1], device=dev), torch.zeros(shape[1], device=dev), 32, 1e-5, silu=True)
         ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float(), 32))
         assert (y.float() - ref).abs().max() < 3e-2
+    # two-source GroupNorm (cat-free up-block ResNets): fused and two-pass paths, group straddling the source boundary
+    for shp in [(2, 64, 128, 5, 7), (1, 8, 56, 3, 3)]:
+        xa = rnd(shp[0], shp[1], shp[3], shp[4]).to(bf).contiguous(memory_format=torch.channels_last)
+        xb = rnd(shp[0], shp[2], shp[3], shp[4]).to(bf).contiguous(memory_format=torch.channels_last)
+        Cc = shp[1] + shp[2]
+        y = ops.group_norm(xa, torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev), 32, 1e-5, silu=True, x2=xb)
+        ref = torch.nn.functional.silu(torch.nn.functional.group_norm(torch.cat([xa, xb], 1).float(), 32))
+        assert (y.float() - ref).abs().max() < 3e-2
     # LayerNorm, fused residual + LayerNorm, residual add, GEGLU
     x = rnd(3, 5, 64).to(bf)
     ops.layer_norm(x, torch.ones(64, device=dev), torch.zeros(64, device=dev), 1e-5)

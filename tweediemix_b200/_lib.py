@@ -33,6 +33,7 @@ SIGNATURES = {
     "tmx_groupnorm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tmx_groupnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "tmx_groupnorm_set_variant": (_i, [_i]),
+    "tmx_groupnorm_cat_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "tmx_groupnorm_launches": (_i, [_i, _i, _i, _i, _i]),
     "tmx_resadd_fwd": (_i, [_vp, _vp, _vp, _sz, _f, _i, _vp]),
     "tmx_bias_resadd_fwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),

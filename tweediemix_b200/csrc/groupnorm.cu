@@ -57,6 +57,26 @@ __device__ __forceinline__ float silu_fast(float y) {
 template <typename T> __device__ __forceinline__ float silu_for(float y) { return sizeof(T) == 2 ? silu_fast(y) : silu(y); }
 
 
+
+// Two-source input (the channel concatenation [x | x2] of an up-block ResNet, never materialised): channel vector tx of row r lives
+// in x (row stride C1) when tx*8 < C1, else in x2 (row stride C - C1).  x2 == nullptr: one source with row stride C.
+template <typename T>
+struct GnSrc {
+    const T* col;       // this thread's channel vector at pixel 0 of sample n
+    size_t cs;          // row (pixel) stride of its source, in elements
+    __device__ __forceinline__ GnSrc(const T* x, const T* x2, int C, int C1, int HW, int n, int tx) {
+        const int c0 = tx * 8;
+        if (x2 != nullptr && c0 >= C1) { cs = (size_t)(C - C1); col = x2 + (size_t)n * HW * cs + (c0 - C1); }
+        else { cs = (size_t)(x2 != nullptr ? C1 : C); col = x + (size_t)n * HW * cs + c0; }
+    }
+};
+// value of channel c at pixel 0 of sample n (pivot of the shifted sums)
+template <typename T>
+__device__ __forceinline__ float gn_first(const T* x, const T* x2, int C, int C1, int HW, int n, int c) {
+    if (x2 != nullptr && c >= C1) return to_f32<T>(x2[(size_t)n * HW * (C - C1) + (c - C1)]);
+    return to_f32<T>(x[(size_t)n * HW * (x2 != nullptr ? C1 : C) + c]);
+}
+
 // Per-CTA reduction of the per-thread channel sums (S, SS)[8] to per-group sums, deterministic order.
 // sh: [8][RY][CV] float2 (conflict-free: consecutive threads write consecutive words), then [C] float2 channel totals.
 // Stage A: the first CV threads add the RY row lanes of their 8 channels; stage B: one warp per group adds its cpg
@@ -97,7 +117,7 @@ __device__ __forceinline__ void gn_cta_group_sums(float2* sh, const float (&S)[8
 // re-reducing the partials in every CTA.
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads, 2)
-gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __restrict__ part,
+gn_stats_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const float* __restrict__ add, float2* __restrict__ part,
               float2* __restrict__ stat, unsigned int* __restrict__ tickets,
               int C, int HW, int G, int rows_per_cta, float eps) {
     extern __shared__ float2 sh[];                      // [8][RY][CV] partials + [C] channel totals (gn_cta_group_sums)
@@ -108,8 +128,9 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
     const int n = blockIdx.y, P = gridDim.x;
     const int row0 = blockIdx.x * rows_per_cta;
     const int row1 = min(HW, row0 + rows_per_cta);
-    const T* xn = x + (size_t)n * HW * C;
-    const T* col = xn + (size_t)tx * 8;
+    const GnSrc<T> src(x, x2, C, C1, HW, n, tx);
+    const T* col = src.col;
+    const size_t cs = src.cs;
 
     // first batch of row loads goes out before anything else (the pivot staging below overlaps it)
     int r = row0 + ty;
@@ -117,11 +138,11 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
     const bool full0 = (sizeof(T) == 2) && (r + 3 * RY < row1);
     if (full0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) q[u] = ld_keep(col + (size_t)(r + u * RY) * C);
+        for (int u = 0; u < 4; ++u) q[u] = ld_keep(col + (size_t)(r + u * RY) * cs);
     }
     // pivot = x'[n, pixel 0, first channel of the group]: sums of (x' - pivot) do not cancel
     for (int g = threadIdx.x; g < G; g += blockDim.x)
-        s_piv[g] = to_f32<T>(xn[g * cpg]) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
+        s_piv[g] = gn_first<T>(x, x2, C, C1, HW, n, g * cpg) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
     __syncthreads();
     float kk[8], S[8], SS[8];
 #pragma unroll
@@ -138,7 +159,7 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
                 uint4 qn[4];
                 if (more) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) qn[u] = ld_keep(col + (size_t)(rn + u * RY) * C);
+                    for (int u = 0; u < 4; ++u) qn[u] = ld_keep(col + (size_t)(rn + u * RY) * cs);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -156,7 +177,7 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
     }
     for (; r < row1; r += RY) {
         float f0[8];
-        V8<T>::load(col + (size_t)r * C, f0, true);
+        V8<T>::load(col + (size_t)r * cs, f0, true);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d0 = f0[j] - kk[j]; S[j] += d0; SS[j] = fmaf(d0, d0, SS[j]); }
     }
@@ -187,22 +208,23 @@ gn_stats_nhwc(const T* __restrict__ x, const float* __restrict__ add, float2* __
 
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads, 2)
-gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+gn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ add, const float2* __restrict__ stat, T* __restrict__ y,
               int C, int HW, int G, int rows_per_cta, int act) {
     const int CV = C >> 3, RY = blockDim.x / CV, cpg = C / G;
     const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
     const int n = blockIdx.y;
-    const T* xn = x + (size_t)n * HW * C;
     const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
-    const T* col = xn + (size_t)tx * 8;
+    const GnSrc<T> src(x, x2, C, C1, HW, n, tx);
+    const T* col = src.col;
+    const size_t cs = src.cs;
     T* ycol = y + (size_t)n * HW * C + (size_t)tx * 8;
     int r = row0 + ty;
     uint4 q[4];
     const bool full0 = (sizeof(T) == 2) && (r + 3 * RY < row1);
     if (full0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) q[u] = ld_stream(col + (size_t)(r + u * RY) * C);
+        for (int u = 0; u < 4; ++u) q[u] = ld_stream(col + (size_t)(r + u * RY) * cs);
     }
     float a[8], b[8];
 #pragma unroll
@@ -221,7 +243,7 @@ gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
                 uint4 qn[4];
                 if (more) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * C);
+                    for (int u = 0; u < 4; ++u) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * cs);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -243,7 +265,7 @@ gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
     }
     for (; r < row1; r += RY) {
         float f[8];
-        V8<T>::load(col + (size_t)r * C, f, false);
+        V8<T>::load(col + (size_t)r * cs, f, false);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float v = fmaf(f[j], a[j], b[j]);
@@ -260,7 +282,7 @@ gn_apply_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
 // sync[n] = arrival counter of batch row n (left at zero), sync[1024 + n] = barrier generation (zero-initialised once).
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads, 1)
-gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+gn_fused_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ add, float2* __restrict__ part, float2* __restrict__ stat,
               unsigned int* __restrict__ sync, T* __restrict__ y,
               int C, int HW, int G, int rows_per_cta, float eps, int act) {
@@ -274,8 +296,9 @@ gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
     const int row1 = min(HW, row0 + rows_per_cta);
     uint4* slab = gn_smem;
     float2* sh = reinterpret_cast<float2*>(gn_smem + (size_t)rows_per_cta * CV);
-    const T* xn = x + (size_t)n * HW * C;
-    const T* col = xn + (size_t)tx * 8;
+    const GnSrc<T> src(x, x2, C, C1, HW, n, tx);
+    const T* col = src.col;
+    const size_t cs = src.cs;
     const bool active = ty < RY;                          // blockDim.x == CV * RY exactly, kept for clarity
     unsigned int* cnt = sync + n;
     unsigned int* gen = sync + 1024 + n;
@@ -286,9 +309,9 @@ gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
     int r = row0 + ty;
     uint4 q[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) if (active && r + u * RY < row1) q[u] = ld_stream(col + (size_t)(r + u * RY) * C);
+    for (int u = 0; u < 8; ++u) if (active && r + u * RY < row1) q[u] = ld_stream(col + (size_t)(r + u * RY) * cs);
     for (int g = threadIdx.x; g < G; g += blockDim.x)
-        s_piv[g] = to_f32<T>(xn[g * cpg]) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
+        s_piv[g] = gn_first<T>(x, x2, C, C1, HW, n, g * cpg) + (add ? add[(size_t)n * C + g * cpg] : 0.f);
     __syncthreads();
     float kk[8], S[8], SS[8];
 #pragma unroll
@@ -301,7 +324,7 @@ gn_fused_nhwc(const T* __restrict__ x, const float* __restrict__ gamma, const fl
         const int rn = r + 8 * RY;
         uint4 qn[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) if (rn + u * RY < row1) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * C);
+        for (int u = 0; u < 8; ++u) if (rn + u * RY < row1) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * cs);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (r + u * RY < row1) {
@@ -529,7 +552,8 @@ static size_t gn_align(size_t v) { return (v + 15) & ~(size_t)15; }
 
 template <typename T>
 static int run_gn(const void* x, const float* gamma, const float* beta, const float* add, void* y, void* ws,
-                  int N, int C, int HW, int G, float eps, int act, int layout, cudaStream_t st) {
+                  int N, int C, int HW, int G, float eps, int act, int layout, cudaStream_t st,
+                  const void* x2v = nullptr, int C1 = 0) {
     unsigned int* tickets = (unsigned int*)ws;
     float2* stat = (float2*)((char*)ws + kGnTicketBytes);
     float* pivots = (float*)((char*)stat + gn_align((size_t)N * G * sizeof(float2)));
@@ -539,10 +563,11 @@ static int run_gn(const void* x, const float* gamma, const float* beta, const fl
             GnFusedPlan fp = plan_fused(N, C, HW);
             if (fp.ok && g_gn_force_two_pass != 1) {
                 const T* xx = (const T*)x; T* yy = (T*)y;
+                const T* xx2 = (const T*)x2v;
                 unsigned int* sync = tickets;
-                void* args[] = {&xx, &gamma, &beta, &add, &part, &stat, &sync, &yy, &C, &HW, &G, &fp.rows_per_cta, &eps, &act};
+                void* args[] = {&xx, &xx2, &C1, &gamma, &beta, &add, &part, &stat, &sync, &yy, &C, &HW, &G, &fp.rows_per_cta, &eps, &act};
                 if (g_gn_force_two_pass == 2) {
-                    gn_fused_nhwc<T><<<dim3(fp.P, N), fp.threads, fp.smem, st>>>(xx, gamma, beta, add, part, stat, sync, yy, C, HW, G, fp.rows_per_cta, eps, act);
+                    gn_fused_nhwc<T><<<dim3(fp.P, N), fp.threads, fp.smem, st>>>(xx, xx2, C1, gamma, beta, add, part, stat, sync, yy, C, HW, G, fp.rows_per_cta, eps, act);
                     return check_cuda(cudaGetLastError(), "gn_fused_nhwc launch");
                 }
                 cudaError_t e = cudaLaunchCooperativeKernel((void*)gn_fused_nhwc<T>, dim3(fp.P, N), dim3(fp.threads), args, fp.smem, st);
@@ -554,9 +579,9 @@ static int run_gn(const void* x, const float* gamma, const float* beta, const fl
         GnPlan p = plan_nhwc(N, C, HW);
         dim3 grid(p.P, N);
         size_t smem = ((size_t)p.RY * C + C) * sizeof(float2);
-        gn_stats_nhwc<T><<<grid, p.threads, smem, st>>>((const T*)x, add, part, stat, tickets, C, HW, G, p.rows_per_cta, eps);
+        gn_stats_nhwc<T><<<grid, p.threads, smem, st>>>((const T*)x, (const T*)x2v, C1, add, part, stat, tickets, C, HW, G, p.rows_per_cta, eps);
         TMX_CUDA(cudaGetLastError());
-        gn_apply_nhwc<T><<<grid, p.threads, 0, st>>>((const T*)x, gamma, beta, add, stat, (T*)y, C, HW, G, p.rows_per_cta, act);
+        gn_apply_nhwc<T><<<grid, p.threads, 0, st>>>((const T*)x, (const T*)x2v, C1, gamma, beta, add, stat, (T*)y, C, HW, G, p.rows_per_cta, act);
         return check_cuda(cudaGetLastError(), "gn_apply_nhwc launch");
     }
     const int cpg = C / G, nvec = cpg * HW / 8;
@@ -635,4 +660,20 @@ extern "C" int tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
     }
     set_error("groupnorm: unsupported dtype %d", dtype);
     return TMX_EDTYPE;
+}
+
+extern "C" int tmx_groupnorm_cat_fwd(const void* x1, const void* x2, int C1, const float* gamma, const float* beta, const float* add,
+                                     void* y, void* workspace, int N, int C, int HW, int G, float eps, int act, int dtype, void* stream) {
+    TMX_REQUIRE(x1 && x2 && gamma && beta && y && workspace, TMX_EINVAL, "groupnorm_cat: null pointer");
+    TMX_REQUIRE(N > 0 && C > 0 && HW > 0 && G > 0 && N <= 1024, TMX_EINVAL, "groupnorm_cat: bad size");
+    TMX_REQUIRE(C1 > 0 && C1 < C && C1 % 8 == 0 && C % 8 == 0, TMX_ESHAPE, "groupnorm_cat: C1=%d must be a multiple of 8 inside (0, C=%d)", C1, C);
+    TMX_REQUIRE(G <= 64 && C % G == 0, TMX_ESHAPE, "groupnorm_cat: C=%d not divisible by G=%d (G<=64)", C, G);
+    TMX_REQUIRE(C / 8 <= kGnMaxThreads && gn_row_lanes(C / 8) > 0, TMX_ESHAPE, "groupnorm_cat: no warp-aligned block for C=%d", C);
+    TMX_REQUIRE(act == TMX_ACT_NONE || act == TMX_ACT_SILU, TMX_EINVAL, "groupnorm_cat: bad act %d", act);
+    TMX_REQUIRE(dtype == TMX_F16 || dtype == TMX_BF16, TMX_EDTYPE, "groupnorm_cat: dtype %d unsupported (fp16/bf16 NHWC only)", dtype);
+    TMX_REQUIRE(aligned16(x1) && aligned16(x2) && aligned16(y) && aligned16(workspace), TMX_EALIGN, "groupnorm_cat: 16-byte alignment");
+    if (int rc = require_init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TMX_F16) return run_gn<__half>(x1, gamma, beta, add, y, workspace, N, C, HW, G, eps, act, TMX_NHWC, st, x2, C1);
+    return run_gn<__nv_bfloat16>(x1, gamma, beta, add, y, workspace, N, C, HW, G, eps, act, TMX_NHWC, st, x2, C1);
 }

@@ -216,30 +216,50 @@ def _workspace(dev: int, nbytes: int) -> torch.Tensor:
     return ws
 
 
-def group_norm(x, gamma, beta, groups: int, eps: float, *, silu=False, add=None, out=None):
+def group_norm(x, gamma, beta, groups: int, eps: float, *, silu=False, add=None, out=None, x2=None):
     """GroupNorm(+add[n,c] before the norm)(+SiLU).  ``x`` is a 4-D NCHW-shaped tensor that is either
-    contiguous (NCHW memory) or channels_last (NHWC memory); the output has the same memory format."""
-    d = _dev(x, gamma, beta, add, out)
+    contiguous (NCHW memory) or channels_last (NHWC memory); the output has the same memory format.
+    ``x2`` (channels_last 16-bit, same N/H/W): normalise the channel concatenation ``cat([x, x2], 1)`` without materialising it."""
+    d = _dev(x, gamma, beta, add, out, x2)
     N, Cc, H, W = x.shape
-    if x.is_contiguous():
+    if x.is_contiguous() and x2 is None:
         layout = _lib.NCHW
     elif x.is_contiguous(memory_format=torch.channels_last):
         layout = _lib.NHWC
     else:
         raise RuntimeError("tmx.group_norm: x must be contiguous or channels_last")
+    C1 = Cc
+    if x2 is not None:
+        if not (x2.is_contiguous(memory_format=torch.channels_last) and x2.dtype == x.dtype and x2.shape[0] == N and tuple(x2.shape[2:]) == (H, W)):
+            raise RuntimeError("tmx.group_norm: x2 must be channels_last with x's dtype, batch and spatial size")
+        if x.dtype not in (torch.float16, torch.bfloat16) or Cc % 8 != 0:
+            raise RuntimeError("tmx.group_norm: the two-source form needs 16-bit inputs and C1 % 8 == 0")
+        Cc = C1 + x2.shape[1]
     if out is None:
-        out = torch.empty_like(x)          # preserves the memory format
-    assert out.stride() == x.stride() and out.dtype == x.dtype
-    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32, "gamma/beta must be fp32"
+        out = torch.empty_like(x) if x2 is None else torch.empty((N, Cc, H, W), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+    assert out.dtype == x.dtype and (out.stride() == x.stride() if x2 is None else (out.shape[1] == Cc and out.is_contiguous(memory_format=torch.channels_last)))
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == Cc, "gamma/beta must be fp32 [C]"
     if add is not None:
         assert add.dtype == torch.float32 and add.is_contiguous() and add.shape == (N, Cc)
     lib = _lib.load()
     ws = _workspace(d, lib.tmx_groupnorm_workspace_bytes(N, Cc, H * W, groups, layout))
-    with _Launch("groupnorm", lib.tmx_groupnorm_launches(N, Cc, H * W, layout, _dt(x)), f"C{Cc}_HW{H * W}", 2.0 * x.numel() * x.element_size()):
-        rc = lib.tmx_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(add), _p(out), _p(ws), N, Cc, H * W, groups,
-                                   float(eps), _lib.ACT_SILU if silu else _lib.ACT_NONE, layout, _dt(x), _stream())
+    nbytes = 2.0 * N * Cc * H * W * x.element_size()
+    with _Launch("groupnorm", lib.tmx_groupnorm_launches(N, Cc, H * W, layout, _dt(x)), f"C{Cc}_HW{H * W}" + ("_cat" if x2 is not None else ""), nbytes):
+        if x2 is None:
+            rc = lib.tmx_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(add), _p(out), _p(ws), N, Cc, H * W, groups,
+                                       float(eps), _lib.ACT_SILU if silu else _lib.ACT_NONE, layout, _dt(x), _stream())
+        else:
+            rc = lib.tmx_groupnorm_cat_fwd(_p(x), _p(x2), C1, _p(gamma), _p(beta), _p(add), _p(out), _p(ws), N, Cc, H * W, groups,
+                                           float(eps), _lib.ACT_SILU if silu else _lib.ACT_NONE, _dt(x), _stream())
     _lib.check(rc, "tmx_groupnorm_fwd")
     return out
+
+
+def cat_free_supported(a, b) -> bool:
+    """Can ``group_norm(a, x2=b)`` stand in for a GroupNorm over ``cat([a, b], 1)``?  (16-bit channels_last CUDA tensors, C % 8 == 0)"""
+    return (a.is_cuda and b.is_cuda and a.dtype == b.dtype and a.dtype in (torch.float16, torch.bfloat16)
+            and a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0
+            and a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last))
 
 
 # ------------------------------------------------------------------------------------------ k6

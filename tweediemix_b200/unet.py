@@ -29,6 +29,7 @@ Dense GEMMs / convolutions that the north star leaves to libraries go to cuBLASL
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -78,6 +79,7 @@ class UNetConfig:
 
 
 HEAD_DIM = 64
+CAT_FREE = os.environ.get("TMX_CAT_FREE", "1") != "0"     # up blocks read (hidden, skip) as two sources instead of torch.cat (A/B switch)
 
 
 def _tokens(x4: torch.Tensor) -> torch.Tensor:
@@ -135,9 +137,9 @@ class TmxGroupNorm(nn.GroupNorm):
             self._b32 = self.bias.detach().float().contiguous()
         return self._w32, self._b32
 
-    def forward(self, x, silu: bool = False, add: Optional[torch.Tensor] = None):  # type: ignore[override]
+    def forward(self, x, silu: bool = False, add: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None):  # type: ignore[override]
         w, b = self._params32()
-        return ops.group_norm(x, w, b, self.num_groups, self.eps, silu=silu, add=add)
+        return ops.group_norm(x, w, b, self.num_groups, self.eps, silu=silu, add=add, x2=x2)
 
 
 class TimestepEmbedding(nn.Module):
@@ -478,11 +480,29 @@ class ResnetBlock2D(nn.Module):
             b = self.__dict__["_tail_bias"] = b.contiguous()
         return b
 
-    def forward(self, x, temb_all):
+    def shortcut_halves(self, c1: int):
+        """1x1 shortcut weights split at input channel ``c1``: conv_shortcut(cat([a, b])) = a @ Wa.T + b @ Wb.T."""
+        hit = self.__dict__.get("_sc_halves")
+        w = self.conv_shortcut.weight
+        if hit is None or hit[0] != c1 or hit[1].device != w.device or hit[1].dtype != w.dtype:
+            w2 = w.detach().reshape(w.shape[0], w.shape[1])
+            hit = self.__dict__["_sc_halves"] = (c1, w2[:, :c1].contiguous(), w2[:, c1:].contiguous())
+        return hit[1], hit[2]
+
+    def forward(self, x, temb_all, x2: Optional[torch.Tensor] = None):
+        """``x2``: the skip tensor of an up block — the block computes on ``cat([x, x2], 1)`` without materialising it: norm1 reads
+        both sources (k4/k5 two-source form) and the 1x1 shortcut is two GEMMs accumulating into one output."""
         # conv1.bias rides in temb_all (packed with time_emb_proj.bias), conv2/shortcut biases in the tail add
-        h = _conv_nobias(self.conv1, self.norm1(x, silu=True))
+        h = _conv_nobias(self.conv1, self.norm1(x, silu=True, x2=x2))
         h = _conv_nobias(self.conv2, self.norm2(h, silu=True, add=temb_all[self.temb_slice_index]))
-        if self.conv_shortcut is not None:
+        if x2 is not None:
+            wa, wb = self.shortcut_halves(x.shape[1])
+            _, _, hh, ww = x.shape
+            ta, tb = _tokens(x), _tokens(x2)
+            s_ = F.linear(ta, wa)                                             # [B, HW, cout]
+            s_.view(-1, s_.shape[-1]).addmm_(tb.reshape(-1, tb.shape[-1]), wb.t())   # cuBLAS beta = 1: accumulates in place
+            x = _image(s_, hh, ww)
+        elif self.conv_shortcut is not None:
             x = _conv_nobias(self.conv_shortcut, x)
         return ops.bias_residual_add(h, self.tail_bias(), x, 1.0 / self.output_scale_factor, out=h)
 
@@ -571,7 +591,11 @@ class UpBlock(nn.Module):
 
     def forward(self, h, temb_all, ehs, skips):
         for i, res in enumerate(self.resnets):
-            h = res(torch.cat([h, skips.pop()], dim=1), temb_all)
+            skip = skips.pop()
+            if CAT_FREE and res.conv_shortcut is not None and ops.cat_free_supported(h, skip):
+                h = res(h, temb_all, x2=skip)                                 # no torch.cat: 9 copies of up to 126 MB per forward
+            else:
+                h = res(torch.cat([h, skip], dim=1), temb_all)
             if self.attentions is not None:
                 h = self.attentions[i](h, ehs)
         if self.upsamplers is not None:
@@ -655,6 +679,7 @@ class TmxUNet2DConditionModel(nn.Module):
                 m.__dict__.pop("_p32", None)
             elif isinstance(m, ResnetBlock2D):
                 m.__dict__.pop("_tail_bias", None)
+                m.__dict__.pop("_sc_halves", None)
         self._temb_w = self._temb_b = None
         _F32_CACHE.clear()
         return self
