@@ -174,3 +174,19 @@ def test_sampler_under_other_gemm_policies(monkeypatch, lora, impl):
     rel = (got - want).abs().max().item() / want.abs().max().item()
     print(f"sampler parity lora={lora} fp16 TMX_GEMM={impl}: rel_max={rel:.3e}")
     assert s.n_forward_rows == orc.n_forward_rows and rel <= TOL_LOOP[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_cat_free_up_blocks_gpu(monkeypatch, dtype):
+    """TMX_CAT_FREE=1 (two-source GroupNorm + split shortcut GEMMs in the up blocks) vs the default torch.cat path and the fp32 oracle."""
+    from tweediemix_b200 import unet as U
+    ref = synth.make_base_unet(T.RCFG, 1)
+    prod = _gpu_unet(ref, dtype)
+    x, E, cond = T._inputs(4, hw=32)
+    want = ref(x, 781, E, cond)["sample"]
+    cc = {k: v.cuda() for k, v in cond.items()}
+    base = prod(x.cuda(), 781, E.cuda(), cc)["sample"]
+    monkeypatch.setattr(U, "CAT_FREE", True)
+    got = prod(x.cuda(), 781, E.cuda(), cc)["sample"]
+    assert _rel(got, want) <= TOL_FWD[dtype]
+    assert (got.float() - base.float()).abs().max().item() <= 0.5 * TOL_FWD[dtype] * want.abs().max().item()

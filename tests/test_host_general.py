@@ -178,3 +178,21 @@ def test_gemm_policies_match_oracle(monkeypatch, lora, impl):
     prod.init_fusion(int(n * 0.2), int(n * 0.8)) if lora else prod.init_fusion(int(n * 0.2))
     got = prod.sample_loop(x0.clone())
     assert (got - want).abs().max().item() < 1e-3
+
+
+def test_cat_free_up_blocks_match_oracle(monkeypatch):
+    """TMX_CAT_FREE=1: the up-block ResNets take (hidden, skip) as two sources (two-source GroupNorm, split 1x1 shortcut) instead of
+    torch.cat — same function."""
+    fake_ops.install(monkeypatch)
+    from tweediemix_b200 import unet as U
+    monkeypatch.setattr(U, "CAT_FREE", True)
+    ref = synth.make_base_unet(T.RCFG, 1)
+    prod = T.product_unet(ref)
+    x, E, cond = T._inputs(4)
+    want = ref(x, 781, E, cond)["sample"]
+    calls = []
+    real = U.ops.group_norm
+    monkeypatch.setattr(U.ops, "group_norm", lambda *a, **k: (calls.append(k.get("x2") is not None), real(*a, **k))[1])
+    got = prod(x, 781, E, cond)["sample"]
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    assert sum(calls) == 9                                  # the nine up-block ResNets

@@ -60,7 +60,7 @@ bias_resadd_kernel(const T* __restrict__ a, const T* __restrict__ b, const float
 // stays in registers: 2 reads + 2 writes instead of (2R + 1W) + (1R + 1W) and one launch instead of two.
 // The statistics are taken from the ROUNDED h, i.e. exactly the tensor the un-fused LayerNorm would read.
 template <typename T, int NV>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)      // 4 CTAs / SM = 592 resident CTAs: the 512 CTAs of a 4 x 1024-token site run as ONE wave (60 registers, no spills)
 resadd_layernorm_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ gamma,
                         const float* __restrict__ beta, T* __restrict__ h_out, T* __restrict__ n_out,
                         long long rows, int D, float eps) {

@@ -79,7 +79,10 @@ class UNetConfig:
 
 
 HEAD_DIM = 64
-CAT_FREE = os.environ.get("TMX_CAT_FREE", "1") != "0"     # up blocks read (hidden, skip) as two sources instead of torch.cat (A/B switch)
+# TMX_CAT_FREE=1: up-block ResNets read (hidden, skip) as two sources (two-source GroupNorm + the 1x1 shortcut as two accumulating GEMMs)
+# instead of torch.cat.  Measured on B200 (profiles/r02k_bench*.json): 32.15 vs 31.95 ms per fused step — the 0.5 ms of cat copies saved
+# are paid back by the shortcut's second pass over its output, so the default stays torch.cat + one cuDNN 1x1 conv; opt-in.
+CAT_FREE = os.environ.get("TMX_CAT_FREE", "0") == "1"
 
 
 def _tokens(x4: torch.Tensor) -> torch.Tensor:
