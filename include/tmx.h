@@ -246,7 +246,7 @@ TMX_API int tmx_linear_fwd(const void* x, const void* w, const float* bias, cons
  * first 4 KiB ONCE (the kernels re-arm their counters), pass it to every call; NULL disables the split (whole tiles only). */
 TMX_API size_t tmx_linear_workspace_bytes(void);
 
-/* Tuning / test hook: tile width of tmx_linear_fwd (0 = heuristic, 128, 192, 256), + 1000 to disable the split-K tail,
+/* Tuning / test hook: tile width of tmx_linear_fwd (0 = heuristic, 128, 192, 256, 320), + 1000 to disable the split-K tail,
  * + 2000 to take it at any K (default: only when K >= 2560). */
 TMX_API int tmx_linear_set_variant(int v);
 

@@ -32,7 +32,7 @@ SHAPES = [  # M, N, K
 ]
 
 
-@pytest.mark.parametrize("bn", [0, 128, 192, 256, 1000, 1256])      # + 1000: split-K tail disabled
+@pytest.mark.parametrize("bn", [0, 128, 192, 256, 320, 1000, 1256])      # + 1000: split-K tail disabled
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_linear_bias_residual(shape, dtype, bn):
@@ -78,7 +78,7 @@ def test_linear_geglu_epilogue(shape, dtype, bn):
         _variant(0)
 
 
-@pytest.mark.parametrize("bn", [0, 128, 192, 256, 1256])
+@pytest.mark.parametrize("bn", [0, 128, 192, 256, 320, 1256])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("B,Mb,N,K,nseg", [(4, 1024, 3840, 1280, 3), (4, 1024, 1280, 1280, 1), (3, 4096, 1920, 640, 3), (2, 128, 64, 64, 1), (1, 1024, 1280, 1280, 1)])
 def test_linear_lora_tail(B, Mb, N, K, nseg, dtype, bn):

@@ -224,7 +224,7 @@ def main():
             rs = [torch.randn(M, N, device=dev, dtype=DT) for _ in range(nb)] if epi == "res" else None
             ys = [torch.empty(M, n_out, device=dev, dtype=DT) for _ in range(nb)]
             fl = 2.0 * M * N * K
-            for bn in (0, 128, 192, 256, 1000, 2256):        # + 1000 = split-K tail disabled, + 2000 = split-K tail at any K
+            for bn in (0, 128, 192, 256, 320, 1000):         # + 1000 = split-K tail disabled (+ 2000 = split-K tail at any K)
                 assert lib.tmx_linear_set_variant(bn) == 0
                 us = timeit(lambda i: ops.linear(xs[i], w, bias, residual=rs[i] if rs else None, geglu=epi == "geglu", out=ys[i]), nb, args.reps)
                 out.append(("linear" if bn == 0 else f"linear:v{bn}", f"{tag}_{epi or 'bias'} x{cnt if bn == 0 else 0}", us, fl / us / 1e6, "TFLOP/s", tf))

@@ -68,7 +68,7 @@ def main():
     # k10: ragged M / N tiles, both tile widths, bias + residual, GEGLU, LoRA tail (+ the t = x . down^T kernel)
     from tweediemix_b200 import _lib
     from tweediemix_b200.routing import LoRARouting
-    for bn in (128, 192, 256):
+    for bn in (128, 192, 256, 320):
         assert _lib.load().tmx_linear_set_variant(bn) == 0
         xa, wa = rnd(300, 192).to(bf), (rnd(328, 192) / 14).to(bf)
         ba, ra = rnd(328), rnd(300, 328).to(bf)

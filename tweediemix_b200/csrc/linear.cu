@@ -39,14 +39,17 @@ constexpr int kMaxTailTiles = 256;              // > any SM count: tail tiles < 
 constexpr int kMaxSplit = 8;
 
 template <int BN> struct Cfg {
-    static constexpr int kBTile = BN * kBK * 2;                  // 16 / 24 / 32 KiB
-    static constexpr int kStages = BN == 128 ? 5 : 4;
-    static constexpr int kRing = kStages * (kATile + kBTile);    // 160 / 160 / 192 KiB
+    static constexpr int kBTile = BN * kBK * 2;                  // 16 / 24 / 32 / 40 KiB
+    static constexpr int kStages = BN == 128 ? 5 : (BN == 320 ? 3 : 4);
+    static constexpr int kRing = kStages * (kATile + kBTile);    // 160 / 160 / 192 / 168 KiB
     static constexpr int kStage = 2 * kSlab;                     // staging tile: 128 rows x 128 columns, 32 KiB
     static constexpr int kBars = 2 * kStages + 4 + 1;
     static constexpr int kSmem = 1024 + kRing + kStage + kBars * 8 + 16;
-    static constexpr int kTmemCols = BN == 128 ? 256 : 512;      // two accumulator stages of BN columns (power of two)
-    static constexpr int kHalves = (BN + 127) / 128;             // BN = 192: the second half holds 64 columns
+    static constexpr int kTmemCols = BN == 128 ? 256 : 512;      // accumulator stages of BN columns (power of two)
+    static constexpr int kAccStages = 2 * BN <= 512 ? 2 : 1;     // BN = 320: one 320-column accumulator (single-wave shapes: nothing to overlap)
+    static constexpr int kHalves = (BN + 127) / 128;             // BN = 192 / 320: the last half holds 64 columns
+    static constexpr int kNMma = BN > 256 ? 2 : 1;               // UMMA N <= 256: a 320-wide tile is two N = 160 instructions per K step
+    static constexpr int kN = BN / kNMma;
 };
 
 __device__ unsigned int g_k10_timeout_flag = 0;
@@ -248,7 +251,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 if (elect_one()) {
                     mbar_expect_tx(full + 8 * st, kATile + C::kBTile);
                     tma_load_2d(sA + st * kATile, &tm_x, full + 8 * st, kt * kBK, mt * kBM);
-                    tma_load_2d(sB + st * C::kBTile, &tm_w, full + 8 * st, kt * kBK, nt * BN);
+#pragma unroll
+                    for (int m = 0; m < C::kNMma; ++m)                  // (TMA boxes hold <= 256 rows: a 320-wide W tile is two boxes)
+                        tma_load_2d(sB + st * C::kBTile + m * (C::kN * 128), &tm_w, full + 8 * st, kt * kBK, nt * BN + m * C::kN);
                 }
                 K10_NEXT(st, ph, NST);
             }
@@ -259,7 +264,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                     if (elect_one()) {
                         mbar_expect_tx(full + 8 * st, kATile + C::kBTile);
                         tma_load_2d(sA + st * kATile, &tm_t, full + 8 * st, 0, mt * kBM);
-                        tma_load_2d(sB + st * C::kBTile, &tm_up.m[b], full + 8 * st, 0, nt * BN);
+#pragma unroll
+                        for (int m = 0; m < C::kNMma; ++m)
+                            tma_load_2d(sB + st * C::kBTile + m * (C::kN * 128), &tm_up.m[b], full + 8 * st, 0, nt * BN + m * C::kN);
                     }
                     K10_NEXT(st, ph, NST);
                 }
@@ -267,14 +274,16 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // =========================================== MMA issuer =============================================
-        constexpr uint32_t idesc = make_idesc(BF16, kBM, BN);
+        constexpr uint32_t idesc = make_idesc(BF16, kBM, C::kN);
+        constexpr uint32_t kBHalf = (uint32_t)(C::kN * 128) >> 4;       // descriptor offset of the second N = kN half of the W tile
         int st = 0;
         uint32_t ph = 0;
         Item it;
         for (int i = 0; get_item(p, i, KT, it); ++i) {
-            const uint32_t a = (uint32_t)i & 1u;
+            const uint32_t a = C::kAccStages == 2 ? ((uint32_t)i & 1u) : 0u;
+            const uint32_t use = C::kAccStages == 2 ? ((uint32_t)i >> 1) : (uint32_t)i;
             const int mt = it.tile % p.MT;
-            mbar_wait(acc_empty + 8 * a, (((uint32_t)i >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator stage
+            mbar_wait(acc_empty + 8 * a, (use & 1u) ^ 1u);                // the epilogue has drained this accumulator stage
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + a * BN;
             for (int kt = 0; kt < it.kn; ++kt) {
@@ -282,10 +291,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a_lo = desc_lo(sA + st * kATile), b_lo = desc_lo(sB + st * C::kBTile);
-                    umma_ss(d_tmem, a_lo, b_lo, idesc, kt > 0 ? 1u : 0u);
-                    umma_ss(d_tmem, a_lo + 2, b_lo + 2, idesc, 1u);
-                    umma_ss(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
-                    umma_ss(d_tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+#pragma unroll
+                    for (int m = 0; m < C::kNMma; ++m) {
+                        umma_ss(d_tmem + m * C::kN, a_lo, b_lo + m * kBHalf, idesc, kt > 0 ? 1u : 0u);
+                        umma_ss(d_tmem + m * C::kN, a_lo + 2, b_lo + m * kBHalf + 2, idesc, 1u);
+                        umma_ss(d_tmem + m * C::kN, a_lo + 4, b_lo + m * kBHalf + 4, idesc, 1u);
+                        umma_ss(d_tmem + m * C::kN, a_lo + 6, b_lo + m * kBHalf + 6, idesc, 1u);
+                    }
                     umma_commit(empty + 8 * st);
                 }
                 K10_NEXT(st, ph, NST);
@@ -296,7 +308,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                     mbar_wait(full + 8 * st, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        umma_ss(d_tmem, desc_lo(sA + st * kATile), desc_lo(sB + st * C::kBTile), idesc, it.kn > 0 ? 1u : 0u);
+#pragma unroll
+                        for (int m = 0; m < C::kNMma; ++m)
+                            umma_ss(d_tmem + m * C::kN, desc_lo(sA + st * kATile), desc_lo(sB + st * C::kBTile) + m * kBHalf, idesc, it.kn > 0 ? 1u : 0u);
                         umma_commit(empty + 8 * st);
                     }
                     K10_NEXT(st, ph, NST);
@@ -452,9 +466,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         nx.tile = 0;
         if (p.has_res && leader && get_item(p, 0, KT, it) && it.s < 0) load_residual(it.tile / p.MT, it.tile % p.MT, 0);
         for (int i = 0; get_item(p, i, KT, it); ++i) {
-            const uint32_t a = (uint32_t)i & 1u;
+            const uint32_t a = C::kAccStages == 2 ? ((uint32_t)i & 1u) : 0u;
+            const uint32_t use = C::kAccStages == 2 ? ((uint32_t)i >> 1) : (uint32_t)i;
             const int nt = it.tile / p.MT, mt = it.tile - nt * p.MT;
-            mbar_wait(acc_full + 8 * a, ((uint32_t)i >> 1) & 1u);
+            mbar_wait(acc_full + 8 * a, use & 1u);
             tc_fence_after();
             const uint32_t t_acc = t_row + a * BN + cg * 64;
             if (it.s < 0) {
@@ -647,7 +662,7 @@ static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split, int
     const int q = (int)(tiles / sms), r = (int)(tiles % sms);
     int S = 0;
     const bool eager = g_split_mode == 2;                              // tuning hook: split whenever a slice keeps >= 4 K blocks
-    if (can_split && r > 0 && (KT >= kMinSplitKT || eager) && bn != 192) {
+    if (can_split && r > 0 && (KT >= kMinSplitKT || eager) && bn != 192 && bn != 320) {
         S = sms / r;
         if (S > kMaxSplit) S = kMaxSplit;
         const int min_slice = eager ? 4 : kMinSliceK;
@@ -657,10 +672,11 @@ static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split, int
     // Cost model fitted to profiles/r02j_kbench_linear.txt.  A tile takes the longer of its main loop — KT K-blocks of four
     // MMAs at bn/2 clk each, slowed by the shared-memory operand bandwidth for narrower tiles (0.78 / 0.93 of the 256-wide rate) —
     // and its epilogue (~4000 clk per 128 columns, more with a residual or the GEGLU gating), which bounds the K = 640 shapes.
-    const double rate = bn == 256 ? 1.0 : (bn == 192 ? 0.93 : 0.78);
+    const double rate = bn == 256 ? 1.0 : (bn == 320 ? 0.95 : (bn == 192 ? 0.93 : 0.78));
     const double main_clk = KT * 2.0 * bn / rate;
     const double epi_clk = bn / 128.0 * (4000.0 + (has_res ? 1000.0 : 0.0) + (epilogue == TMX_EPI_GEGLU ? 2000.0 : 0.0));
-    const double tile_clk = main_clk > epi_clk ? main_clk : epi_clk;
+    // one accumulator stage (320-wide tiles): the epilogue of a tile does not overlap the next main loop
+    const double tile_clk = bn == 320 ? (q + (r > 0) > 1 ? main_clk + epi_clk : main_clk) : (main_clk > epi_clk ? main_clk : epi_clk);
     double rounds;
     if (S >= 2) {
         pl.full_tiles = q * sms; pl.split = S; pl.tail_units = r * S;
@@ -679,7 +695,8 @@ static Plan make_plan(int M, int N, int KT, int bn, int sms, bool can_split, int
 static Plan pick_plan(int M, int N, int KT, int epilogue, bool has_res, bool can_split) {
     const int sms = sm_count();
     can_split = can_split && g_split_mode != 1;
-    if (g_force_bn == 128 || g_force_bn == 192 || g_force_bn == 256) return make_plan(M, N, KT, g_force_bn, sms, can_split, epilogue, has_res);
+    if (g_force_bn == 320 && epilogue == TMX_EPI_GEGLU) return make_plan(M, N, KT, 256, sms, can_split, epilogue, has_res);
+    if (g_force_bn == 128 || g_force_bn == 192 || g_force_bn == 256 || g_force_bn == 320) return make_plan(M, N, KT, g_force_bn, sms, can_split, epilogue, has_res);
     Plan best = make_plan(M, N, KT, N <= 128 ? 128 : 256, sms, can_split, epilogue, has_res);
     if (N > 128) {
         const Plan p128 = make_plan(M, N, KT, 128, sms, can_split, epilogue, has_res);
@@ -687,6 +704,10 @@ static Plan pick_plan(int M, int N, int KT, int epilogue, bool has_res, bool can
         if (epilogue != TMX_EPI_GEGLU) {                               // (a 192-wide GEGLU tile would end in half an output slab)
             const Plan p192 = make_plan(M, N, KT, 192, sms, can_split, epilogue, has_res);
             if (p192.cost < best.cost * 0.97) best = p192;
+            if (N > 256) {                                             // 320-wide single-accumulator tiles: the N = 1280 / 640 shapes in ONE or two waves
+                const Plan p320 = make_plan(M, N, KT, 320, sms, can_split, epilogue, has_res);
+                if (p320.cost < best.cost * 0.97) best = p320;
+            }
         }
     }
     return best;
@@ -705,7 +726,7 @@ int linear_init() {
     }
 #define K10_KATTR(B16, BN, SP) TMX_CUDA(cudaFuncSetAttribute(linear_kernel<B16, BN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem))
     K10_KATTR(true, 128, false); K10_KATTR(false, 128, false); K10_KATTR(true, 192, false); K10_KATTR(false, 192, false);
-    K10_KATTR(true, 256, false); K10_KATTR(false, 256, false);
+    K10_KATTR(true, 256, false); K10_KATTR(false, 256, false); K10_KATTR(true, 320, false); K10_KATTR(false, 320, false);
     K10_KATTR(true, 128, true); K10_KATTR(false, 128, true); K10_KATTR(true, 256, true); K10_KATTR(false, 256, true);
 #undef K10_KATTR
 #define K10_ATTR(T, SR) TMX_CUDA(cudaFuncSetAttribute(lora_t_kernel<T, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
@@ -723,8 +744,8 @@ using namespace tmx::k10;
 extern "C" int tmx_linear_set_variant(int v) {
     // v = tile width (0 auto, 128, 256) + 1000 to disable the split-K tail
     const int bn = v % 1000, nosplit = v / 1000;
-    TMX_REQUIRE(v >= 0 && (bn == 0 || bn == 128 || bn == 192 || bn == 256) && nosplit <= 2, TMX_EINVAL,
-                "linear_set_variant: 0 | 128 | 192 | 256 (+ 1000 = no split-K tail, + 2000 = split-K tail at any K)");
+    TMX_REQUIRE(v >= 0 && (bn == 0 || bn == 128 || bn == 192 || bn == 256 || bn == 320) && nosplit <= 2, TMX_EINVAL,
+                "linear_set_variant: 0 | 128 | 192 | 256 | 320 (+ 1000 = no split-K tail, + 2000 = split-K tail at any K)");
     g_force_bn = bn;
     g_split_mode = nosplit;
     return TMX_OK;
@@ -768,7 +789,8 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
     CUtensorMap mx, mw, my, mr, mt;
     UpMaps ups;
     if (int rc = encode2d(&mx, x, (uint64_t)K, (uint64_t)M, (uint64_t)ldx, kBM, bf16)) return rc;
-    if (int rc = encode2d(&mw, w, (uint64_t)K, (uint64_t)N, (uint64_t)K, (uint32_t)BN, bf16)) return rc;
+    const uint32_t w_box = (uint32_t)(BN > 256 ? BN / 2 : BN);          // TMA boxes hold <= 256 rows
+    if (int rc = encode2d(&mw, w, (uint64_t)K, (uint64_t)N, (uint64_t)K, w_box, bf16)) return rc;
     if (int rc = encode2d(&my, y, (uint64_t)n_out, (uint64_t)M, (uint64_t)ldy, kBM, bf16)) return rc;
     mr = my; mt = mx;
     if (residual) { if (int rc = encode2d(&mr, residual, (uint64_t)N, (uint64_t)M, (uint64_t)ldr, kBM, bf16)) return rc; }
@@ -782,7 +804,7 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
         for (int b = 0; b < lora_batch; ++b) {
             if (!lora_up[b]) continue;
             TMX_REQUIRE(aligned16(lora_up[b]), TMX_EALIGN, "linear: lora_up[%d] alignment", b);
-            if (int rc = encode2d(&ups.m[b], lora_up[b], 64, (uint64_t)N, 64, (uint32_t)BN, bf16)) return rc;
+            if (int rc = encode2d(&ups.m[b], lora_up[b], 64, (uint64_t)N, 64, w_box, bf16)) return rc;
             p.tail_mask |= 1u << b;
         }
         p.has_tail = p.tail_mask != 0;
@@ -793,10 +815,11 @@ extern "C" int tmx_linear_fwd(const void* x, const void* w, const float* bias, c
     const void* fn = nullptr;
 #define K10_PICK(BNv, SPv) (bf16 ? (const void*)linear_kernel<true, BNv, SPv> : (const void*)linear_kernel<false, BNv, SPv>)
     if (BN == 256) fn = sp ? K10_PICK(256, true) : K10_PICK(256, false);
+    else if (BN == 320) fn = K10_PICK(320, false);
     else if (BN == 192) fn = K10_PICK(192, false);
     else fn = sp ? K10_PICK(128, true) : K10_PICK(128, false);
 #undef K10_PICK
-    const size_t smem = BN == 256 ? Cfg<256>::kSmem : (BN == 192 ? Cfg<192>::kSmem : Cfg<128>::kSmem);
+    const size_t smem = BN == 320 ? Cfg<320>::kSmem : (BN == 256 ? Cfg<256>::kSmem : (BN == 192 ? Cfg<192>::kSmem : Cfg<128>::kSmem));
     void* args[] = {&mx, &mw, &my, &mr, &mt, &ups, &p};
     if (pl.split >= 2) {
         // the K-slices of a tail tile wait for each other: the grid (<= one CTA per SM) must be co-resident
