@@ -69,6 +69,37 @@ def test_attention_matches_oracle(shape, nq, dtype):
     assert err <= ATOL[dtype], f"max|diff| {err}"
 
 
+SPLIT_SHAPES = [  # units cut along K/V between CTAs (stream-K schedule): 2-4 pieces per unit, an odd tile count, one row per GPU
+    (1, 5, 200, 333), (1, 3, 300, 700), (2, 2, 128, 2000), (1, 1, 256, 4096), (1, 20, 1024, 1024), (1, 10, 4096, 4096), (2, 20, 1024, 1024),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sched", [20, 21, 22])   # whole tiles / cost model / always split
+@pytest.mark.parametrize("shape", SPLIT_SHAPES)
+def test_attention_split_schedule(shape, sched, dtype):
+    """The three schedules agree with the oracle; a second launch (flags re-armed by the owners) is bit-identical to the first."""
+    o = ops()
+    from tweediemix_b200 import _lib
+    B, H, Nq, Nk = shape
+    g = torch.Generator().manual_seed(Nq + 5 * Nk + H)
+    q = torch.randn(B, Nq, H * 64, generator=g).to(dtype).cuda()
+    k = (2.0 * torch.randn(B, Nk, H * 64, generator=g)).to(dtype).cuda()      # peaked rows: the pieces of a unit see different maxima
+    v = torch.randn(B, Nk, H * 64, generator=g).to(dtype).cuda()
+    _lib.load().tmx_attn_set_variant(sched)
+    try:
+        got = o.attention(q, k, v, H)
+        again = o.attention(q, k, v, H)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().tmx_attn_set_variant(0)
+    want = _ref(q, k, v, H)
+    assert torch.isfinite(got.float()).all()
+    assert torch.equal(got, again)
+    err = (got.float() - want).abs().max().item()
+    assert err <= ATOL[dtype], f"max|diff| {err}"
+
+
 def test_attention_large_logits_and_strided_qkv():
     """Peaked softmax (|logit| ~ 60: exercises the running-max / lazy-rescale path) and q/k/v given as
     column slices of one fused [B, N, 3*H*64] projection output (token stride 3*H*64)."""

@@ -64,11 +64,14 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--attn-variant", type=int, default=0, help="tmx_attn_set_variant() value (11 / 12 = one / two softmax threads per row)")
     ap.add_argument("--gn-variant", type=int, default=0, help="tmx_groupnorm_set_variant(): 0 fused cooperative, 1 two launches, 2 fused plain launch")
+    ap.add_argument("--batch", type=int, default=4, help="U-Net batch rows (4 = one K=3 fused step on one GPU; 2 / 1 = the per-rank batch of a 2- / 4-rank concept-parallel group)")
     ap.add_argument("--shapes", default="", help="comma-separated substrings; only shapes whose tag contains one are run (profiling aid)")
     ap.add_argument("--compare", action="store_true",
                     help="also time the same-box library kernels for the same shapes (measurement only, never a product dependency): "
                          "F.scaled_dot_product_attention, flash-attn, F.group_norm+F.silu, F.layer_norm, F.linear (cuBLAS)")
     args = ap.parse_args()
+    global B
+    B = args.batch
     if args.gn_variant:
         from tweediemix_b200 import _lib
         build.build()

@@ -25,6 +25,16 @@ def main():
         ref = torch.nn.functional.scaled_dot_product_attention(
             q.view(B, Nq, H, 64).transpose(1, 2).float(), k.view(B, Nk, H, 64).transpose(1, 2).float(), v.view(B, Nk, H, 64).transpose(1, 2).float())
         assert (o.float() - ref.transpose(1, 2).reshape(B, Nq, H * 64)).abs().max() < 3e-2
+    # stream-K schedule forced on: units of 6 K/V tiles cut into 3 pieces each (dump -> flag -> merge path)
+    from tweediemix_b200 import _lib as _l
+    _l.load().tmx_attn_set_variant(22)
+    for (B, H, Nq, Nk) in [(1, 2, 200, 700), (1, 1, 300, 333)]:
+        q, k, v = rnd(B, Nq, H * 64).to(bf), rnd(B, Nk, H * 64).to(bf), rnd(B, Nk, H * 64).to(bf)
+        o = ops.attention(q, k, v, H)
+        ref = torch.nn.functional.scaled_dot_product_attention(
+            q.view(B, Nq, H, 64).transpose(1, 2).float(), k.view(B, Nk, H, 64).transpose(1, 2).float(), v.view(B, Nk, H, 64).transpose(1, 2).float())
+        assert (o.float() - ref.transpose(1, 2).reshape(B, Nq, H * 64)).abs().max() < 3e-2
+    _l.load().tmx_attn_set_variant(0)
     # GroupNorm: fused (NHWC 16-bit), two-pass (fp32), NCHW
     for shape, dt, cl in [((2, 64, 5, 7), bf, True), ((3, 320, 9, 9), bf, True), ((1, 32, 1, 8), torch.float32, True), ((2, 64, 4, 6), bf, False)]:
         x = rnd(*shape).to(dt)

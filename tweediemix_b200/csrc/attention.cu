@@ -1,12 +1,18 @@
 // k1 / k2 — attention forward for head_dim 64 on sm_100a:  O = softmax(scale * Q K^T) V.
 //
 // Blackwell-native structure (no mma.sync / wgmma):
-//   * PERSISTENT: one 384-thread CTA per SM walks a contiguous, balanced range of 128-row query
-//     tiles (linear index over (b, h, q-tile)); two query tiles of the same (b, h) are processed
-//     together ("slots" 0 and 1) and share every K/V tile, a lone tile at a range or head boundary
-//     runs in slot 0 alone.  The next step's Q (double-buffered) and K/V tiles are prefetched while
-//     the current step computes, so there is no per-tile prologue bubble and the tail of the launch
-//     is at most one lone query tile per SM;
+//   * PERSISTENT, STREAM-K SCHEDULED: the work is the linear space of (unit, K/V tile) iterations,
+//     a unit being two 128-row query tiles of one (b, h) that are processed together ("slots" 0 and
+//     1) and share every K/V tile (a lone last tile of an odd count runs in slot 0 alone).  One
+//     384-thread CTA per SM takes an EQUAL contiguous share of that space, so a unit may be cut
+//     along its K/V axis between neighbouring CTAs: the CTA holding the head of a unit owns it, the
+//     others leave their un-normalised partial (O, m, l) in a global workspace (a CTA's first
+//     piece, so it is ready long before the owner — whose head piece comes LAST in its range —
+//     asks for it) and the owner folds them in during its epilogue, in CTA order (deterministic).
+//     Every SM gets the same number of tile iterations whatever B*H*tiles is, instead of whole
+//     query tiles quantised over 148 SMs (measured before: 5 vs 4.3 steps at B=4 / N=4096, and
+//     the same 2 steps at B=2 as at B=4 for N=1024).  The next step's Q (double-buffered) and K/V
+//     tiles are prefetched while the current step computes: no per-step prologue bubble;
 //   * Q, K, V tiles are staged global -> shared by TMA (cp.async.bulk.tensor.4d, SWIZZLE_128B)
 //     straight from the [B, N, H, 64] tensors diffusers hands the hook, no permute;
 //   * S = Q K^T and O += P V are tcgen05.mma (kind::f16, M=128) issued by ONE elected thread per
@@ -314,26 +320,142 @@ constexpr int kBars = 6 * kSlots + 2 * kQBufs * kSlots + 4 * kStages;
 constexpr int kSmemBytes = 1024 /*align slack*/ + (kQBufs * kSlots + 2 * kStages + kSlots /*O staging*/) * kTileBytes + kBars * 8 + 16
                            + 2 * kSlots * 2 * kBM * 4 /*l_xchg*/ + 2 * kSlots * 2 * kBM * 4 /*m_xchg (HV == 2 with -DTMX_ATTN_HV2_XCHG)*/;
 
-// One scheduling step of a CTA: query tile `qt` (and qt+1 when nslots == 2) of head h, batch b.
-struct Step { int b, h, qt, nslots; };
+// One scheduling step of a CTA: K/V tiles [j0, j1) of the unit that begins at schedule index `start` (nslots query tiles).
+// A step with j0 == 0 && j1 == T is a whole unit; j0 > 0 is a partial piece handed to the unit's owner through the workspace;
+// j0 == 0 && j1 < T is the owner's head piece.  The (b, h, query tile) coordinates are decoded from `start` only where they
+// are needed (TMA loads / the one thread that issues the store): the softmax warps have no registers to spare for them.
+struct Step { int start, nslots, j0, j1; };
 
-// Walk the CTA's range [it, end) of linear query-tile ids; QT = query tiles per (b, h).
-__device__ __forceinline__ bool next_step(int& it, int end, int QT, int H, int pair, Step& s) {
+// Walk the CTA's range [it, end).  split == 1: linear (unit, K/V tile) iterations, UPP = units per (b, h), TPU = query tiles per
+// unit.  split == 0: linear query-tile ids (whole tiles only); pairs are formed greedily inside the range, a lone tile at a range
+// or head boundary runs in slot 0 alone.
+__device__ __forceinline__ bool next_step(int& it, int end, int split, int T, int QT, int UPP, int TPU, Step& s) {
     if (it >= end) return false;
-    const int bh = it / QT;
-    s.qt = it - bh * QT;
-    s.b = bh / H;
-    s.h = bh - s.b * H;
-    s.nslots = (pair && it + 1 < end && s.qt + 1 < QT) ? 2 : 1;
-    it += s.nslots;
+    s.start = it;
+    if (split) {
+        const int u = it / T;
+        s.j0 = it - u * T;
+        const int left = end - it;
+        s.j1 = left < T - s.j0 ? s.j0 + left : T;
+        const int qt = (u % UPP) * TPU;
+        s.nslots = (TPU == 2 && qt + 1 < QT) ? 2 : 1;
+        it += s.j1 - s.j0;
+    } else {
+        s.j0 = 0;
+        s.j1 = T;
+        s.nslots = (TPU == 2 && it + 1 < end && it % QT + 1 < QT) ? 2 : 1;
+        it += s.nslots;
+    }
     return true;
+}
+__device__ __forceinline__ void step_coords(int start, int split, int T, int QT, int UPP, int TPU, int H, int& b, int& h, int& qt) {
+    int bh;
+    if (split) {
+        const int u = start / T;
+        bh = u / UPP;
+        qt = (u - bh * UPP) * TPU;
+    } else {
+        bh = start / QT;
+        qt = start - bh * QT;
+    }
+    b = bh / H;
+    h = bh - b * H;
+}
+
+// Split-unit workspace, per CTA and slot: O[kD][kBM] fp32 (column-major: a warp writes 32 consecutive rows of one
+// column), then m[kBM] (reference max, log2 domain) and l[kBM] (row sum against that reference).
+constexpr int kWsFloatsPerSlot = (kD + 2) * kBM;
+
+__device__ __forceinline__ void flag_wait(const unsigned int* f) {
+    unsigned int v;
+    long long t0 = 0;
+    unsigned int polls = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v != 0) return;
+        if ((++polls & 255u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) { atomicExch(&g_attn_timeout_flag, 2u); __trap(); }
+        }
+    }
+}
+
+// Cold paths of the split-unit protocol, kept out of line so that they do not add to the register pressure of the softmax loop.
+// Hand a partial piece to the unit's owner: (O, m, l) of this thread's row, un-normalised, into the CTA's workspace slot.
+__device__ __noinline__ void split_dump(float* wsp, unsigned int* flag, uint32_t t_o, int row, float m_ref, float l_sum, int bar_id, bool signal) {
+    wsp[kD * kBM + row] = m_ref;
+    wsp[(kD + 1) * kBM + row] = l_sum;
+#pragma unroll
+    for (int g = 0; g < kD / 32; ++g) {
+        uint32_t o[32];
+        tmem_ld32(t_o + g * 32, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) wsp[(g * 32 + c) * kBM + row] = __uint_as_float(o[c]);
+    }
+#ifndef TMX_SPLIT_NOFENCE
+    __threadfence();
+#endif
+    asm volatile("bar.sync %0, 128;" :: "r"(bar_id) : "memory");
+    if (signal) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(1u) : "memory");
+}
+// Owner of a unit whose tail went to the following CTA(s): fold their partials into the owner's own (O in TMEM at t_o, m_ref,
+// l_sum), one piece after the other in CTA order, each piece fetched as ONE batch of independent L2 loads (m, l and the 64 O
+// columns of the row), then normalise and write the row into the swizzled staging tile (o_row) like the plain epilogue does.
+// Returns the index behind the last piece.
+template <bool BF16>
+__device__ __noinline__ int split_merge(const float* ws_slot0, const unsigned int* flags_slot0, int first, int unit_end, int total_iters,
+                                        uint32_t t_o, int row, int lane, float m_run, float l_run, uint32_t o_row) {
+    float o[kD];
+    {
+        uint32_t r[32];
+#pragma unroll
+        for (int g = 0; g < kD / 32; ++g) {
+            tmem_ld32(t_o + g * 32, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[g * 32 + c] = __uint_as_float(r[c]);
+        }
+    }
+    int k = first;
+    for (; k < (int)gridDim.x && (int)(((long long)k * total_iters) / gridDim.x) < unit_end; ++k) {
+#ifndef TMX_SPLIT_NOWAIT
+        if (lane == 0) flag_wait(flags_slot0 + k * kSlots);
+        __syncwarp();
+#endif
+        const float* wk = ws_slot0 + (size_t)k * kSlots * kWsFloatsPerSlot + row;
+        float v[kD];
+#pragma unroll
+        for (int c = 0; c < kD; ++c) v[c] = __ldcg(wk + c * kBM);
+        const float mk = __ldcg(wk + kD * kBM), lk = __ldcg(wk + (kD + 1) * kBM);
+        const float m_new = fmaxf(m_run, mk);
+        const float a_own = ex2(m_run - m_new), a_k = ex2(mk - m_new);
+        l_run = l_run * a_own + lk * a_k;
+        m_run = m_new;
+#pragma unroll
+        for (int c = 0; c < kD; ++c) o[c] = fmaf(v[c], a_k, o[c] * a_own);
+    }
+    const float inv_l = 1.f / l_run;
+    const uint32_t o_sw = (uint32_t)(row & 7);
+#pragma unroll
+    for (int c = 0; c < kD; c += 8) {
+        uint4 q;
+        q.x = pack2<BF16>(o[c] * inv_l, o[c + 1] * inv_l);
+        q.y = pack2<BF16>(o[c + 2] * inv_l, o[c + 3] * inv_l);
+        q.z = pack2<BF16>(o[c + 4] * inv_l, o[c + 5] * inv_l);
+        q.w = pack2<BF16>(o[c + 6] * inv_l, o[c + 7] * inv_l);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(o_row + ((((uint32_t)c >> 3) ^ o_sw) << 4)), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+    }
+    return k;
 }
 
 template <bool BF16, int HV>
 __global__ void __launch_bounds__(AttnCfg<HV>::kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
-                int Nq, int Nk, int H, int QT, int total_tiles, int pair, float scale_log2) {
+                int Nq, int Nk, int H, int QT, int UPP, int TPU, int total_iters, int split,
+                float* __restrict__ ws, unsigned int* __restrict__ ws_flags, float scale_log2) {
     using Cfg = AttnCfg<HV>;
     constexpr int ST = kStages;
     constexpr int kUtilWarp = Cfg::kUtilWarp;
@@ -366,8 +488,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int T = (Nk + kBN - 1) / kBN;                   // K/V tiles per step
     const int last_valid = Nk - (T - 1) * kBN;            // valid kv rows of the last tile (1..128)
-    const int tile_begin = (int)(((long long)blockIdx.x * total_tiles) / gridDim.x);
-    const int tile_end = (int)(((long long)(blockIdx.x + 1) * total_tiles) / gridDim.x);
+    // this CTA's equal share of the schedule space (split: (unit, K/V tile) iterations, else query tiles); total_iters is its size
+    const int tile_begin = (int)(((long long)blockIdx.x * total_iters) / gridDim.x);
+    const int tile_end = (int)(((long long)(blockIdx.x + 1) * total_iters) / gridDim.x);
 
     if (warp == kUtilWarp + 1 && lane == 0) {
         for (int i = 0; i < kQBufs * kSlots; ++i) { mbar_init(q_full + 8u * (i), 1); mbar_init(q_empty + 8u * (i), 1); }
@@ -397,29 +520,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 int st = 0;
                 uint32_t ph = 0;
                 TMX_TRACE_DECL(0, lane == 0)
-                while (next_step(it, tile_end, QT, H, pair, cur)) {
+                while (next_step(it, tile_end, split, T, QT, UPP, TPU, cur)) {
                     const int buf = (int)(sidx & 1u);
+                    int cb, ch, cqt;
+                    step_coords(cur.start, split, T, QT, UPP, TPU, H, cb, ch, cqt);
                     for (int w = 0; w < cur.nslots; ++w) {
                         const int qi = buf * kSlots + w;
                         mbar_wait(q_empty + 8u * (qi), ((qbits >> qi) & 1u) ^ 1u);
                         qbits ^= 1u << qi;
                         if (elect_one()) {
                             mbar_expect_tx(q_full + 8u * (qi), kTileBytes);
-                            tma_load_4d(sQ_a + qi * kTileBytes, &tm_q, q_full + 8u * (qi), 0, cur.h, (cur.qt + w) * kBM, cur.b);
+                            tma_load_4d(sQ_a + qi * kTileBytes, &tm_q, q_full + 8u * (qi), 0, ch, (cqt + w) * kBM, cb);
                         }
                     }
-                    for (int j = 0; j < T; ++j) {
+                    for (int j = cur.j0; j < cur.j1; ++j) {
                         mbar_wait(k_empty + 8u * (st), ph ^ 1u);
                         TMX_TRACE(0);
                         if (elect_one()) {
                             mbar_expect_tx(k_full + 8u * (st), kTileBytes);
-                            tma_load_4d(sK_a + st * kTileBytes, &tm_k, k_full + 8u * (st), 0, cur.h, j * kBN, cur.b);
+                            tma_load_4d(sK_a + st * kTileBytes, &tm_k, k_full + 8u * (st), 0, ch, j * kBN, cb);
                         }
                         mbar_wait(v_empty + 8u * (st), ph ^ 1u);
                         TMX_TRACE(1);
                         if (elect_one()) {
                             mbar_expect_tx(v_full + 8u * (st), kTileBytes);
-                            tma_load_4d(sV_a + st * kTileBytes, &tm_v, v_full + 8u * (st), 0, cur.h, j * kBN, cur.b);
+                            tma_load_4d(sV_a + st * kTileBytes, &tm_v, v_full + 8u * (st), 0, ch, j * kBN, cb);
                         }
                         if (++st == ST) { st = 0; ph ^= 1u; }
                     }
@@ -439,7 +564,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             int st = 0;
             uint32_t ph = 0;
             TMX_TRACE_DECL(1, lane == 0)
-            while (next_step(it, tile_end, QT, H, pair, cur)) {
+            while (next_step(it, tile_end, split, T, QT, UPP, TPU, cur)) {
                 const int buf = (int)(sidx & 1u);
                 const bool two = cur.nslots == 2;
                 {
@@ -448,7 +573,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (two) { mbar_wait(q_full + 8u * (buf * kSlots + 1), (qbits >> (buf * kSlots + 1)) & 1u); qbits ^= 1u << (buf * kSlots + 1); }
                 }
                 const uint32_t a_lo0 = q_lo0 + (uint32_t)(buf * kSlots) * (kTileBytes >> 4);
-                for (int j = 0; j < T; ++j) {
+                for (int j = cur.j0; j < cur.j1; ++j) {
                     const uint32_t b_lo = k_lo0 + (uint32_t)st * (kTileBytes >> 4);
                     mbar_wait(k_full + 8u * (st), ph);
                     TMX_TRACE(10);
@@ -500,9 +625,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             int st = 0;
             uint32_t ph = 0;
             TMX_TRACE_DECL(3, w == 0 && lane == 0)
-            while (next_step(it, tile_end, QT, H, pair, cur)) {
+            while (next_step(it, tile_end, split, T, QT, UPP, TPU, cur)) {
                 const bool act = w < cur.nslots;
-                for (int j = 0; j < T; ++j) {
+                for (int j = cur.j0; j < cur.j1; ++j) {
                     const uint32_t b_lo = v_lo0 + (uint32_t)st * (kTileBytes >> 4);
                     mbar_wait(v_full + 8u * (st), ph);
                     TMX_TRACE(13);
@@ -512,11 +637,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         tc_fence_after();
                         if (elect_one()) {                                 // (K = 16 kv rows): +2048 B in V, +8 columns in P
                             if (j < T - 1 || last_ksteps == kBN / 16) {
-                                umma_ts_lo(t_o, t_p, b_lo, idesc_pv, j > 0 ? 1u : 0u);
+                                umma_ts_lo(t_o, t_p, b_lo, idesc_pv, j > cur.j0 ? 1u : 0u);
 #pragma unroll
                                 for (int k = 1; k < kBN / 16; ++k) umma_ts_lo(t_o, t_p + k * 8, b_lo + k * 128, idesc_pv, 1u);
                             } else {
-                                for (int k = 0; k < last_ksteps; ++k) umma_ts_lo(t_o, t_p + k * 8, b_lo + k * 128, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                                for (int k = 0; k < last_ksteps; ++k) umma_ts_lo(t_o, t_p + k * 8, b_lo + k * 128, idesc_pv, (j > cur.j0 || k > 0) ? 1u : 0u);
                             }
                             umma_commit(pv_done + 8u * (w));
                             umma_commit(v_empty + 8u * (st));
@@ -556,11 +681,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         TMX_TRACE_DECL(2, warp == 0 && lane == 0)
         int it = tile_begin;
         Step cur;
-        while (next_step(it, tile_end, QT, H, pair, cur)) {
+        while (next_step(it, tile_end, split, T, QT, UPP, TPU, cur)) {
             if (w >= cur.nslots) continue;
             float m_ref = -INFINITY;                         // running reference max, log2 domain (scaled)
             float l_sum = 0.f;                               // (partial) row sum over this thread's columns
-            for (int j = 0; j < T; ++j, ++n) {
+            for (int j = cur.j0; j < cur.j1; ++j, ++n) {
                 const bool last = (j == T - 1);
                 const bool partial = last && last_valid < kBN;
                 mbar_wait(bar_s_full, n & 1u);
@@ -622,7 +747,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const bool bump = m_tile > m_ref + kRescaleThreshold;
                 const float m_new = bump ? m_tile : m_ref;
                 bool pv_waited = false;
-                if (j > 0 && __any_sync(0xffffffffu, bump)) {            // warp-uniform: tcgen05.ld/st are warp-collective
+                if (j > cur.j0 && __any_sync(0xffffffffu, bump)) {            // warp-uniform: tcgen05.ld/st are warp-collective
                     mbar_wait(bar_pv_done, (n - 1u) & 1u);               // O must hold every P V issued so far
                     tc_fence_after();
                     pv_waited = true;
@@ -661,7 +786,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (c & 1) sum_b = fadd2(sum_b, pk2(e0, e1)); else sum_a = fadd2(sum_a, pk2(e0, e1));
                     packed = pack2<BF16>(e0, e1);
                 };
-                if (!pv_waited && j > 0) {                                 // P(n-1) must have been consumed before it is overwritten;
+                if (!pv_waited && j > cur.j0) {                                 // P(n-1) must have been consumed before it is overwritten;
                     mbar_wait(bar_pv_done, (n - 1u) & 1u);                 // P V(n-1) was issued a whole load + max phase ago: normally ready
                     tc_fence_after();
                 }
@@ -709,38 +834,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 l_sum += lx[(half ^ 1) * kBM + row];
                 ++nstep;
             }
-            const float inv_l = 1.f / l_sum;
             mbar_wait(bar_pv_done, (n - 1u) & 1u);
             tc_fence_after();
+            if constexpr (HV == 1) {
+                if (cur.j0 > 0) {
+                    // ---- partial piece of a unit owned by an earlier CTA: leave (O, m, l) un-normalised in this CTA's workspace
+                    split_dump(ws + ((size_t)blockIdx.x * kSlots + w) * kWsFloatsPerSlot, ws_flags + blockIdx.x * kSlots + w,
+                               t_row + 128, row, m_ref, l_sum, 11 + w, quarter == 0 && lane == 0);
+                    tc_fence_before();
+                    continue;
+                }
+            }
             // O / l -> 16-bit -> this slot's staging tile (row r = 128 B, 16-byte chunks XOR-swizzled with r & 7) -> ONE TMA store of
             // the 128 x 64 tile: full-line bulk writes instead of 32 scattered 16-byte stores per warp instruction, rows beyond Nq
             // clipped by the tensor map.  Barrier A: the issuing thread has seen its previous store read the tile; barrier B: all rows written.
             const uint32_t o_row = sO_a + w * kTileBytes + row * 128;
             const uint32_t o_sw = (uint32_t)(row & 7);
             asm volatile("bar.sync %0, %1;" :: "r"(11 + w), "n"(128 * HV) : "memory");
+            int k_end = blockIdx.x + 1;                     // pieces [blockIdx.x + 1, k_end) were folded into this unit
+#ifndef TMX_SPLIT_NOMERGE
+            if (HV == 1 && cur.j1 < T) {
+                k_end = split_merge<BF16>(ws + w * kWsFloatsPerSlot, ws_flags + w, blockIdx.x + 1, it + (T - cur.j1) /* `it` already points behind this piece */,
+                                          total_iters, t_row + 128, row, lane, m_ref, l_sum, o_row);
+            } else
+#endif
+            {
+                const float inv_l = 1.f / l_sum;
 #pragma unroll
-            for (int g = 0; g < OC / 32; ++g) {
-                uint32_t o[32];
-                tmem_ld32(t_row + 128 + half * OC + g * 32, o);
-                tc_wait_ld();
+                for (int g = 0; g < OC / 32; ++g) {
+                    uint32_t o[32];
+                    tmem_ld32(t_row + 128 + half * OC + g * 32, o);
+                    tc_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    uint4 v;
-                    v.x = pack2<BF16>(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-                    v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-                    v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-                    v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
-                    const uint32_t chunk = (uint32_t)((half * OC + g * 32 + c) >> 3);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(o_row + ((chunk ^ o_sw) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    for (int c = 0; c < 32; c += 8) {
+                        uint4 v;
+                        v.x = pack2<BF16>(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+                        v.y = pack2<BF16>(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+                        v.z = pack2<BF16>(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+                        v.w = pack2<BF16>(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+                        const uint32_t chunk = (uint32_t)((half * OC + g * 32 + c) >> 3);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(o_row + ((chunk ^ o_sw) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, %1;" :: "r"(13 + w), "n"(128 * HV) : "memory");
             if (half == 0 && quarter == 0 && lane == 0) {
+                int cb, ch, cqt;
+                step_coords(cur.start, split, T, QT, UPP, TPU, H, cb, ch, cqt);
                 asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                             :: "l"(reinterpret_cast<uint64_t>(&tm_o)), "r"(sO_a + w * kTileBytes), "r"(0), "r"(cur.h), "r"((cur.qt + w) * kBM), "r"(cur.b) : "memory");
+                             :: "l"(reinterpret_cast<uint64_t>(&tm_o)), "r"(sO_a + w * kTileBytes), "r"(0), "r"(ch), "r"((cqt + w) * kBM), "r"(cb) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // every row of every piece has been read (barrier B): re-arm the pieces' flags for the next launch
+#ifndef TMX_SPLIT_NOWAIT
+                for (int k = blockIdx.x + 1; k < k_end; ++k) ws_flags[k * kSlots + w] = 0u;
+#endif
             }
             tc_fence_before();           // order the O reads before the next step's P(0) hand-off (p_full arrive)
         }
@@ -760,8 +909,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static float* g_ws[64] = {nullptr};            // per device: split-unit partials, sm_count x kSlots x kWsFloatsPerSlot floats
+static unsigned int* g_ws_flags[64] = {nullptr};
 
 int attn_init() {
+    int dev = 0;
+    TMX_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !g_ws[dev]) {
+        // One workspace per device: launches on DIFFERENT streams of one process must not run this kernel concurrently
+        // (the sampler is single-stream; separate processes have separate contexts and workspaces).
+        const size_t n = (size_t)sm_count() * kSlots;
+        TMX_CUDA(cudaMalloc(&g_ws[dev], n * kWsFloatsPerSlot * sizeof(float)));
+        TMX_CUDA(cudaMalloc(&g_ws_flags[dev], n * sizeof(unsigned int)));
+        TMX_CUDA(cudaMemset(g_ws_flags[dev], 0, n * sizeof(unsigned int)));
+    }
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -794,6 +955,7 @@ static int g_variant = 0;   // test hook: 0 / 2 = pair query tiles (default), 1 
 #define TMX_ATTN_HALVES 1
 #endif
 static int g_halves = TMX_ATTN_HALVES;   // softmax threads per query row (1 or 2)
+static int g_split = 1;                  // stream-K split of units along K/V between CTAs: 0 never, 1 by the cost model, 2 always (test hook: 20 / 21 / 22)
 
 }  // namespace tmx
 
@@ -806,11 +968,12 @@ extern "C" __attribute__((visibility("default"))) int tmx_attn_debug_trace(long 
 #endif
 
 extern "C" int tmx_attn_set_variant(int nq) {
-    // 0: defaults; 1: one query tile per step; 2: pairs; 11 / 12: 1 / 2 softmax threads per query row
+    // 0: defaults; 1: one query tile per step; 2: pairs; 11 / 12: 1 / 2 softmax threads per query row; 20 / 21 / 22: unit split never / by cost / always
     if (nq == 11 || nq == 12) { g_halves = nq - 10; return TMX_OK; }
-    TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1, 2, 11 or 12");
+    if (nq >= 20 && nq <= 22) { g_split = nq - 20; return TMX_OK; }
+    TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1, 2, 11, 12, 20, 21 or 22");
     g_variant = nq;
-    if (nq == 0) g_halves = TMX_ATTN_HALVES;
+    if (nq == 0) { g_halves = TMX_ATTN_HALVES; g_split = 1; }
     return TMX_OK;
 }
 
@@ -831,7 +994,7 @@ extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o
     TMX_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), TMX_EALIGN, "attn: 16-byte alignment");
     const int QT = (Nq + kBM - 1) / kBM;
     const long long total = (long long)B * H * QT;
-    TMX_REQUIRE(total < (1ll << 30), TMX_ESHAPE, "attn: too many query tiles");
+    TMX_REQUIRE(total * ((Nk + kBN - 1) / kBN) < (1ll << 30), TMX_ESHAPE, "attn: too many (query tile, K/V tile) iterations");
     if (int rc = require_init()) return rc;
 
     const bool bf16 = dtype == TMX_BF16;
@@ -842,11 +1005,41 @@ extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (int rc = make_map(&mv, v, B, Nk, H, v_stride_n, bf16)) return rc;
     const float scale_log2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
-    const int pair = g_variant == 1 ? 0 : 1;
-    // persistent grid: one CTA per SM, never more CTAs than (pairs of) query tiles
-    const long long units = pair ? (total + 1) / 2 : total;
-    const int grid = (int)(units < sm_count() ? units : sm_count());
-#define TMX_ATTN_LAUNCH(B16, HV) attn_fwd_kernel<B16, HV><<<grid, AttnCfg<HV>::kThreads, kSmemBytes, st>>>(mq, mk, mv, mo, Nq, Nk, H, QT, (int)total, pair, scale_log2)
+    // Two schedules.  (A) whole query tiles: each CTA an equal contiguous range of tile ids, pairs formed inside the range.
+    // (C) stream-K: units = aligned tile pairs, the (unit, K/V tile) iteration space cut into equal shares, units that straddle
+    // a share boundary merged through the workspace.  C keeps every SM equally busy whatever B*H*tiles is but pays one extra
+    // step per CTA plus the merge; A is quantised to whole tiles.  Pick by a cost model in units of one pair-iteration
+    // (calibrated on `tools/kbench.py --only attention --batch 1|2|4`, profiles/r02p_*): a step costs kStepCost on top of its
+    // iterations, a lone tile kLoneCost of a pair, the merge kMergeCost.
+    const int TPU = g_variant == 1 ? 1 : 2;
+    const int UPP = (QT + TPU - 1) / TPU;
+    const int T = (Nk + kBN - 1) / kBN;
+    const long long units = (long long)B * H * UPP;
+    const int sms = sm_count();
+    int split = 0;
+    if (g_halves == 1 && T > 1 && g_split != 0) {
+        if (g_split == 2) split = 1;
+        else {
+            constexpr float kStepCost = 1.5f, kLoneCost = 0.65f, kMergeCost = 3.0f;
+            const long long unitsA = TPU == 2 ? (total + 1) / 2 : total;
+            const int gridA = (int)(unitsA < sms ? unitsA : sms);
+            const int nt = (int)((total + gridA - 1) / gridA);                  // tiles of the busiest CTA
+            const float costA = TPU == 2 ? (nt / 2 + kLoneCost * (nt & 1)) * T + (nt / 2 + (nt & 1)) * kStepCost : nt * (T + kStepCost);
+            const long long wantC = units * T / 2 > units ? units * T / 2 : units;
+            const int gridC = (int)(wantC < sms ? wantC : sms);
+            const float itersC = (float)(units * T) / gridC;
+            const float costC = itersC + (itersC / T + 1.f) * kStepCost + kMergeCost;
+            split = costC < costA ? 1 : 0;
+        }
+    }
+    const long long iters = split ? units * T : total;
+    long long want = split ? (iters / 2 > units ? iters / 2 : units) : (TPU == 2 ? (total + 1) / 2 : total);
+    const int grid = (int)(want < sms ? want : sms);
+    int dev = 0;
+    TMX_CUDA(cudaGetDevice(&dev));
+    float* ws = g_ws[dev];
+    unsigned int* wf = g_ws_flags[dev];
+#define TMX_ATTN_LAUNCH(B16, HV) attn_fwd_kernel<B16, HV><<<grid, AttnCfg<HV>::kThreads, kSmemBytes, st>>>(mq, mk, mv, mo, Nq, Nk, H, QT, UPP, TPU, (int)iters, split, ws, wf, scale_log2)
     if (g_halves == 2) { if (bf16) TMX_ATTN_LAUNCH(true, 2); else TMX_ATTN_LAUNCH(false, 2); }
     else               { if (bf16) TMX_ATTN_LAUNCH(true, 1); else TMX_ATTN_LAUNCH(false, 1); }
 #undef TMX_ATTN_LAUNCH
