@@ -909,6 +909,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+int short_kv_attn_init();                      // cross_attention.cu
+int short_kv_attn_launch(const void* q, const void* k, const void* v, void* o, int B, int H, int Nq, int Nk,
+                         int64_t q_sn, int64_t k_sn, int64_t v_sn, int64_t o_sn, float scale, bool bf16, int mt, cudaStream_t st);
 static float* g_ws[64] = {nullptr};            // per device: split-unit partials, sm_count x kSlots x kWsFloatsPerSlot floats
 static unsigned int* g_ws_flags[64] = {nullptr};
 
@@ -930,6 +933,7 @@ int attn_init() {
         TMX_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, TMX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
         g_encode = (EncodeTiledFn)fn;
     }
+    if (int rc = short_kv_attn_init()) return rc;
     TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TMX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -955,6 +959,8 @@ static int g_variant = 0;   // test hook: 0 / 2 = pair query tiles (default), 1 
 #define TMX_ATTN_HALVES 1
 #endif
 static int g_halves = TMX_ATTN_HALVES;   // softmax threads per query row (1 or 2)
+static int g_short = 1;                  // K/V sequences of <= 128 rows (cross-attention) go to the streaming kernel of cross_attention.cu with
+                                         // g_short 16-row tiles per warp iteration; 0 = keep them on the tcgen05 kernel (test hook: 30 / 31 / 32)
 static int g_split = 1;                  // stream-K split of units along K/V between CTAs: 0 never, 1 by the cost model, 2 always (test hook: 20 / 21 / 22)
 
 }  // namespace tmx
@@ -971,9 +977,10 @@ extern "C" int tmx_attn_set_variant(int nq) {
     // 0: defaults; 1: one query tile per step; 2: pairs; 11 / 12: 1 / 2 softmax threads per query row; 20 / 21 / 22: unit split never / by cost / always
     if (nq == 11 || nq == 12) { g_halves = nq - 10; return TMX_OK; }
     if (nq >= 20 && nq <= 22) { g_split = nq - 20; return TMX_OK; }
+    if (nq >= 30 && nq <= 32) { g_short = nq - 30; return TMX_OK; }
     TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1, 2, 11, 12, 20, 21 or 22");
     g_variant = nq;
-    if (nq == 0) { g_halves = TMX_ATTN_HALVES; g_split = 1; }
+    if (nq == 0) { g_halves = TMX_ATTN_HALVES; g_split = 1; g_short = 1; }
     return TMX_OK;
 }
 
@@ -998,6 +1005,8 @@ extern "C" int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (int rc = require_init()) return rc;
 
     const bool bf16 = dtype == TMX_BF16;
+    if (Nk <= 128 && g_short != 0 && g_variant == 0 && (long long)B * H <= 65535)
+        return short_kv_attn_launch(q, k, v, o, B, H, Nq, Nk, q_stride_n, k_stride_n, v_stride_n, o_stride_n, scale, bf16, g_short, (cudaStream_t)stream);
     CUtensorMap mq, mk, mv, mo;
     if (int rc = make_map(&mo, o, B, Nq, H, o_stride_n, bf16)) return rc;
     if (int rc = make_map(&mq, q, B, Nq, H, q_stride_n, bf16)) return rc;
