@@ -63,7 +63,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--attn-variant", type=int, default=0, help="tmx_attn_set_variant() value (11 / 12 = one / two softmax threads per row)")
-    ap.add_argument("--gn-variant", type=int, default=0, help="tmx_groupnorm_set_variant(): 0 fused cooperative, 1 two launches, 2 fused plain launch")
+    ap.add_argument("--gn-variant", type=int, default=0, help="tmx_groupnorm_set_variant(): 0 default (per-group slab kernel, else fused cooperative, else two launches), 1 two launches, 2 fused plain launch, 3 per-group slab kernel off")
     ap.add_argument("--batch", type=int, default=4, help="U-Net batch rows (4 = one K=3 fused step on one GPU; 2 / 1 = the per-rank batch of a 2- / 4-rank concept-parallel group)")
     ap.add_argument("--shapes", default="", help="comma-separated substrings; only shapes whose tag contains one are run (profiling aid)")
     ap.add_argument("--compare", action="store_true",
