@@ -6,7 +6,7 @@ mkdir -p $OUT
 python -m tweediemix_b200.build > $OUT/build.log 2>&1
 timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k groupnorm > $OUT/pytest_gn.log 2>&1; echo "pytest gn rc=$?"; tail -4 $OUT/pytest_gn.log | cut -c1-300
 for b in 4 2; do
-  for v in 0; do
+  for v in 0 3; do
     timeout 300 python tools/kbench.py --only groupnorm --batch $b --gn-variant $v > $OUT/kbench_gn_b${b}_v${v}.txt 2>&1; echo "kbench b$b v$v rc=$?"
     grep -E "^groupnorm" $OUT/kbench_gn_b${b}_v${v}.txt | cut -c1-110
   done

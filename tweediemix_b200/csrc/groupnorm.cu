@@ -430,35 +430,49 @@ gn_fused_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
     }
 }
 
-// ------------------------------------------------------------------------- NHWC, one CTA per (sample, group)
-// The (n, g) slab — cpg channels x HW pixels, <= ~200 KB — is owned by ONE CTA: loaded once into shared memory (runs of
-// cpg * 2 bytes per pixel, 8- or 16-byte vectors), reduced inside the CTA, normalised out of shared memory.  No grid barrier, no
-// partials, no cooperative launch: the cost is one launch + one load + one block reduction + one store (measured 2-3x faster
-// than gn_fused_nhwc on the 32x32 / 64x64 SDXL sites, whose 10-40 MB activations are barrier- and launch-latency-bound there).
-// grid (G, N); block = a multiple of lcm(vpp, 32) threads (vpp = vectors per pixel run), so every thread keeps ONE channel vector:
-// its gamma / beta / add and its source (two-source input: [x | x2], never concatenated) are fixed for the whole kernel.
-template <typename T, int VL>        // VL = elements per vector (8: 16-byte loads, cpg % 8 == 0; 4: 8-byte loads, cpg % 4 == 0)
+// ------------------------------------------------------- NHWC, one CTA (or one CLUSTER) per (sample, group)
+// The (n, g) slab — cpg channels x HW pixels — is owned by ONE thread-block cluster of CS = 1, 2, 4 or 8 CTAs, each holding a
+// contiguous range of pixels (<= ~200 KB) in its shared memory: loaded once (runs of cpg * 2 bytes per pixel; 4-, 8- or 16-byte
+// vectors), reduced inside the CTA, the CS partial sums exchanged through DISTRIBUTED shared memory behind a cluster barrier,
+// normalised out of shared memory.  No grid barrier, no partials in global memory, no cooperative launch, x read once and y
+// written once at every SDXL site (the 128x128 sites took two launches and a re-read of x before): the cost is one launch + one
+// load + one block (+ cluster) reduction + one store.
+// grid (G * CS, N), cluster (CS, 1, 1); block = a multiple of lcm(vpp, 32) threads (vpp = vectors per pixel run), so every thread
+// keeps ONE channel vector: its gamma / beta / add and its source (two-source input [x | x2], never concatenated) are fixed.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int VL> struct GnVec;
+template <> struct GnVec<8> { using type = uint4; };
+template <> struct GnVec<4> { using type = uint2; };
+template <> struct GnVec<2> { using type = uint32_t; };
+
+template <typename T, int VL>        // VL = elements per vector: 8 (cpg % 8 == 0), 4 (cpg % 4 == 0) or 2 (cpg % 2 == 0)
 __global__ void __launch_bounds__(1024, 1)
 gn_group_slab(const T* __restrict__ x, const T* __restrict__ x2, int C1, const float* __restrict__ gamma, const float* __restrict__ beta,
-              const float* __restrict__ add, T* __restrict__ y, int C, int HW, int cpg, float eps, int act) {
-    using VT = typename std::conditional<VL == 8, uint4, uint2>::type;
+              const float* __restrict__ add, T* __restrict__ y, int C, int HW, int cpg, int CS, int ppc, float eps, int act) {
+    using VT = typename GnVec<VL>::type;
     extern __shared__ uint4 gn_smem[];
     __shared__ float2 s_red[32];
+    __shared__ float2 s_part;                          // this CTA's shifted sums, read by the whole cluster
     __shared__ float2 s_stat;
     VT* slab = reinterpret_cast<VT*>(gn_smem);
-    const int g = blockIdx.x, n = blockIdx.y;
+    const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int g = blockIdx.x / CS, n = blockIdx.y;
+    const int pbeg = rank * ppc, pend = min(HW, pbeg + ppc);          // this CTA's pixels
     const int vpp = cpg / VL;                          // vectors per pixel run
     const int nt = blockDim.x;                         // multiple of vpp
     const int v = threadIdx.x % vpp;                   // this thread's vector inside the run
     const int c0 = g * cpg + v * VL;                   // its first channel
     const int pstep = nt / vpp;
-    int pix0 = threadIdx.x / vpp;
+    const int pix0 = pbeg + threadIdx.x / vpp;
     // source of this channel vector
     const T* src;
     size_t cs;
     if (x2 != nullptr && c0 >= C1) { cs = (size_t)(C - C1); src = x2 + (size_t)n * HW * cs + (c0 - C1); }
     else { cs = (size_t)(x2 != nullptr ? C1 : C); src = x + (size_t)n * HW * cs + c0; }
-    // pivot of the shifted sums: the group's first channel at pixel 0 (+ its add), the same for every thread of the CTA
+    // pivot of the shifted sums: the group's first channel at pixel 0 (+ its add), the same for every thread of the cluster
     float piv;
     {
         const int cg = g * cpg;
@@ -470,28 +484,29 @@ gn_group_slab(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
 
     auto unpack = [&](const VT& q, float (&f)[VL]) {
         if constexpr (VL == 8) unpack8<T>(q, f);
-        else { float2 a = Pack2<T>::unpack(q.x), b = Pack2<T>::unpack(q.y); f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; }
+        else if constexpr (VL == 4) { float2 a = Pack2<T>::unpack(q.x), b = Pack2<T>::unpack(q.y); f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; }
+        else { float2 a = Pack2<T>::unpack(q); f[0] = a.x; f[1] = a.y; }
     };
-
     auto ldv = [&](int pix) -> VT {
         const T* p = src + (size_t)pix * cs;
         if constexpr (VL == 8) return ld_stream(p);
-        else { uint2 r; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r; }
+        else if constexpr (VL == 4) { uint2 r; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r; }
+        else { uint32_t r; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
     };
-    // ---- phase 1: global -> registers -> (shifted sums, shared slab), 64 bytes in flight per thread.  (Measured: staging the whole
-    // slab by cp.async in one round trip is not faster — 10.1 vs 9.4 us at C=1280, 32x32 — the kernel is bound by launch latency,
-    // the two half-duplex phases of a single CTA per SM and, with SiLU, ~1.4 us of MUFU per 80 KB slab.)
+    // ---- phase 1: global -> registers -> (shifted sums, shared slab), 64 bytes (32 for 4-byte vectors) in flight per thread.
+    // (Measured: staging the whole slab by cp.async in one round trip is not faster — 10.1 vs 9.4 us at C=1280, 32x32 — the
+    // kernel is bound by launch latency, the two half-duplex phases of a CTA and, with SiLU, ~1.4 us of MUFU per 80 KB slab.)
     float S = 0.f, SS = 0.f;
     constexpr int U = VL == 8 ? 4 : 8;
-    for (int pix = pix0; pix < HW; pix += U * pstep) {
+    for (int pix = pix0; pix < pend; pix += U * pstep) {
         VT q[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (pix + u * pstep < HW) q[u] = ldv(pix + u * pstep);
+        for (int u = 0; u < U; ++u) if (pix + u * pstep < pend) q[u] = ldv(pix + u * pstep);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int pp = pix + u * pstep;
-            if (pp < HW) {
-                slab[(size_t)pp * vpp + v] = q[u];
+            if (pp < pend) {
+                slab[(size_t)(pp - pbeg) * vpp + v] = q[u];
                 float f[VL];
                 unpack(q[u], f);
 #pragma unroll
@@ -499,7 +514,7 @@ gn_group_slab(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
             }
         }
     }
-    // ---- block reduction (fixed order: lanes by shuffle tree, warps in index order)
+    // ---- block reduction (fixed order: lanes by shuffle tree, warps in index order), then the cluster's CTAs in rank order
     S = warp_sum(S); SS = warp_sum(SS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nt >> 5;
     if (lane == 0) s_red[warp] = make_float2(S, SS);
@@ -510,12 +525,26 @@ gn_group_slab(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
     if (warp == 0) {
         float2 t = lane < nwarps ? s_red[lane] : make_float2(0.f, 0.f);
         const float s = warp_sum(t.x), ss = warp_sum(t.y);
+        if (lane == 0) s_part = make_float2(s, ss);
+    }
+    if (CS > 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();      // every CTA's s_part is written and visible
+    if (warp == 0) {
+        float s = 0.f, ss = 0.f;
+        if (CS > 1) {
+            if (lane < CS) {                                                     // one DSMEM load per lane, summed by a fixed shuffle tree
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(&s_part)), "r"(lane));
+                asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(s), "=f"(ss) : "r"(remote) : "memory");
+            }
+            s = warp_sum(s); ss = warp_sum(ss);
+        } else { s = s_part.x; ss = s_part.y; }
         if (lane == 0) {
             const float inv = 1.f / ((float)HW * (float)cpg);
             const float md = s * inv;
             s_stat = make_float2(piv + md, rsqrtf(fmaxf(ss * inv - md * md, 0.f) + eps));
         }
     }
+    if (CS > 1) cluster_arrive();                      // "I have read my peers' s_part": waited for at the end, before any CTA may exit
     __syncthreads();
     const float2 st = s_stat;
     float a[VL], b[VL];
@@ -524,9 +553,9 @@ gn_group_slab(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
 
     // ---- phase 2: normalise out of shared memory (each thread re-reads exactly the vectors it wrote: no barrier needed for them)
     T* ycol = y + (size_t)n * HW * C + c0;
-    for (int pix = pix0; pix < HW; pix += pstep) {
+    for (int pix = pix0; pix < pend; pix += pstep) {
         float f[VL];
-        unpack(slab[(size_t)pix * vpp + v], f);
+        unpack(slab[(size_t)(pix - pbeg) * vpp + v], f);
 #pragma unroll
         for (int j = 0; j < VL; ++j) {
             const float val = fmaf(f[j], a[j], b[j]);
@@ -534,11 +563,14 @@ gn_group_slab(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
         }
         T* dst = ycol + (size_t)pix * C;
         if constexpr (VL == 8) st_stream(dst, pack8<T>(f));
-        else {
+        else if constexpr (VL == 4) {
             const uint32_t w0 = Pack2<T>::pack(f[0], f[1]), w1 = Pack2<T>::pack(f[2], f[3]);
             asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(dst), "r"(w0), "r"(w1) : "memory");
+        } else {
+            asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(dst), "r"(Pack2<T>::pack(f[0], f[1])) : "memory");
         }
     }
+    if (CS > 1) cluster_wait();
 }
 
 // ------------------------------------------------------------------------------------------ NCHW
@@ -658,25 +690,52 @@ static GnFusedPlan plan_fused(int N, int C, int HW) {
     return p;
 }
 
-// One CTA per (sample, group): the slab (cpg * HW 16-bit elements) must fit in shared memory, the group's pixel run must be a
-// whole number of 8- or 16-byte vectors, and there must be enough (n, g) pairs to occupy the device.
+// One cluster of CS CTAs per (sample, group): each CTA's share of the slab (cpg * ceil(HW / CS) 16-bit elements) must fit in shared
+// memory, the group's pixel run must be a whole number of 4-, 8- or 16-byte vectors, and there must be enough (n, g) pairs to
+// occupy the device.
 constexpr size_t kGnSlabSmemMax = 208 * 1024;
-struct GnSlabPlan { bool ok; int vl, threads; size_t smem; };
-static int g_gn_slab = 1;                 // test hook (tmx_groupnorm_set_variant 3 / 4): 0 = never take the per-group slab kernel
+struct GnSlabPlan { bool ok; int vl, threads, cs, ppc; size_t smem; };
+static int g_gn_slab = 1;                 // test hook (tmx_groupnorm_set_variant 3 / 4 / 5): 0 = never, 1 = yes, 2 = single CTAs only (no clusters)
 static GnSlabPlan plan_slab(int N, int C, int HW, int G) {
-    GnSlabPlan p{false, 0, 0, 0};
+    GnSlabPlan p{false, 0, 0, 0, 0, 0};
     const int cpg = C / G;
-    if (cpg % 4 != 0 || N > 65535) return p;
-    p.vl = cpg % 8 == 0 ? 8 : 4;
+    if (cpg % 2 != 0 || N > 65535 || (long long)N * G < 24) return p;
+    p.vl = cpg % 8 == 0 ? 8 : (cpg % 4 == 0 ? 4 : 2);
     const int vpp = cpg / p.vl;
     const int unit = vpp / gcd_int(vpp, 32) * 32;             // lcm(vpp, 32)
     if (unit > 1024) return p;
-    p.threads = 1024 / unit * unit;
-    const long long vecs = (long long)HW * vpp;
-    while (p.threads - unit >= 256 && (long long)(p.threads - unit) * 4 >= vecs) p.threads -= unit;    // small slabs: >= 4 vectors per thread
-    p.smem = (size_t)cpg * HW * 2;
-    p.ok = p.smem <= kGnSlabSmemMax && (long long)N * G >= 24;
+    for (int cs = 1; cs <= 8; cs *= 2) {
+        const int ppc = (HW + cs - 1) / cs;
+        const size_t smem = (size_t)cpg * ppc * 2;
+        if (smem > kGnSlabSmemMax) continue;
+        // clusters only with 16-byte vectors: measured (profiles/r02r_kbench_groupnorm_slab.txt) the 128x128 sites (cpg = 10 / 20 / 30:
+        // 4- and 8-byte runs per pixel) are SLOWER per group than the two-launch path with its full-row 16-byte accesses
+        if (cs > 1 && (g_gn_slab == 2 || p.vl != 8 || (long long)(cs - 1) * ppc >= HW)) break;
+        p.cs = cs; p.ppc = ppc; p.smem = smem;
+        p.threads = 1024 / unit * unit;
+        const long long vecs = (long long)ppc * vpp;
+        while (p.threads - unit >= 256 && (long long)(p.threads - unit) * 4 >= vecs) p.threads -= unit;    // small slabs: >= 4 vectors per thread
+        p.ok = true;
+        break;
+    }
     return p;
+}
+
+template <typename T, int VL>
+static int launch_slab(const GnSlabPlan& sp, const void* x, const void* x2, int C1, const float* gamma, const float* beta, const float* add,
+                       void* y, int N, int C, int HW, int G, float eps, int act, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G * sp.cs, N);
+    cfg.blockDim = dim3(sp.threads);
+    cfg.dynamicSmemBytes = sp.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = sp.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sp.cs > 1 ? 1 : 0;
+    return check_cuda(cudaLaunchKernelEx(&cfg, gn_group_slab<T, VL>, (const T*)x, (const T*)x2, C1, gamma, beta, add, (T*)y, C, HW, C / G, sp.cs, sp.ppc, eps, act),
+                      "gn_group_slab launch");
 }
 
 // workspace layout: [tickets + generations: 2048 x u32][stat: N*G x float2][pivots (NCHW path): N*G x f32][part: N*G*kGnMaxParts x float2]
@@ -695,10 +754,9 @@ static int run_gn(const void* x, const float* gamma, const float* beta, const fl
         if constexpr (sizeof(T) == 2) {
             GnSlabPlan sp = plan_slab(N, C, HW, G);
             if (sp.ok && g_gn_slab && g_gn_force_two_pass == 0) {
-                const int cpg = C / G;
-                if (sp.vl == 8) gn_group_slab<T, 8><<<dim3(G, N), sp.threads, sp.smem, st>>>((const T*)x, (const T*)x2v, C1, gamma, beta, add, (T*)y, C, HW, cpg, eps, act);
-                else            gn_group_slab<T, 4><<<dim3(G, N), sp.threads, sp.smem, st>>>((const T*)x, (const T*)x2v, C1, gamma, beta, add, (T*)y, C, HW, cpg, eps, act);
-                return check_cuda(cudaGetLastError(), "gn_group_slab launch");
+                if (sp.vl == 8) return launch_slab<T, 8>(sp, x, x2v, C1, gamma, beta, add, y, N, C, HW, G, eps, act, st);
+                if (sp.vl == 4) return launch_slab<T, 4>(sp, x, x2v, C1, gamma, beta, add, y, N, C, HW, G, eps, act, st);
+                return launch_slab<T, 2>(sp, x, x2v, C1, gamma, beta, add, y, N, C, HW, G, eps, act, st);
             }
             GnFusedPlan fp = plan_fused(N, C, HW);
             if (fp.ok && g_gn_force_two_pass != 1) {
@@ -747,6 +805,8 @@ int groupnorm_init() {
     TMX_CUDA(cudaFuncSetAttribute(gn_group_slab<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSlabSmemMax));
     TMX_CUDA(cudaFuncSetAttribute(gn_group_slab<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSlabSmemMax));
     TMX_CUDA(cudaFuncSetAttribute(gn_group_slab<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSlabSmemMax));
+    TMX_CUDA(cudaFuncSetAttribute(gn_group_slab<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSlabSmemMax));
+    TMX_CUDA(cudaFuncSetAttribute(gn_group_slab<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnSlabSmemMax));
     TMX_CUDA(cudaFuncSetAttribute(gn_fused_nhwc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedSmemMax));
     TMX_CUDA(cudaFuncSetAttribute(gn_fused_nhwc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnFusedSmemMax));
     return TMX_OK;
@@ -759,9 +819,9 @@ using namespace tmx;
 extern "C" int tmx_groupnorm_set_variant(int v) {
     // 0: defaults (per-group slab kernel when the (n, g) slab fits in shared memory, else the cooperative fused kernel when the
     // activation fits in one wave of shared memory, else two launches); 1: always two launches; 2: fused kernel by plain launch;
-    // 3: per-group slab kernel off (fused / two-launch as before); 4: on again
-    TMX_REQUIRE(v >= 0 && v <= 4, TMX_EINVAL, "groupnorm_set_variant: 0 .. 4");
-    if (v == 3 || v == 4) { g_gn_slab = v == 4; return TMX_OK; }
+    // 3: per-group slab kernel off (fused / two-launch as before); 4: on again; 5: on, single CTAs only (no clusters)
+    TMX_REQUIRE(v >= 0 && v <= 5, TMX_EINVAL, "groupnorm_set_variant: 0 .. 5");
+    if (v >= 3) { g_gn_slab = v == 3 ? 0 : (v == 4 ? 1 : 2); return TMX_OK; }
     g_gn_force_two_pass = v;
     if (v == 0) g_gn_slab = 1;
     return TMX_OK;
