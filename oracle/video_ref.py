@@ -109,3 +109,19 @@ def vpred_step_ref(latents, noise_pred, at, at_next, guidance_scale):
     x = at_next.sqrt() * x0 + (1 - at_next).sqrt() * eps
     back = lambda z: z[None, :].reshape(b, f, ch, hh, ww).permute(0, 2, 1, 3, 4)
     return back(x), back(x0)
+
+
+def video_loop_ref(model, latents, unet_forward, alphas_cumprod, final_alpha, timesteps, guidance_scale, injection_timestep, interp):
+    """``pipeline_i2vgen_xl.py:647-656,677-719``: the denoising loop with the reference-style hooks of this module installed
+    (``register_conv_ref``), ``register_time_ref`` per step, both CFG halves through ``unet_forward`` and the step lines."""
+    n = len(timesteps)
+    skip = 1000 // n
+    k = int(n * injection_timestep)
+    schedule = list(timesteps[:k]) if k >= 0 else []
+    register_conv_ref(model, schedule, interp)
+    alpha = lambda t: alphas_cumprod[t] if t >= 0 else final_alpha
+    for t in timesteps:
+        register_time_ref(model, int(t))
+        noise_pred = unet_forward(torch.cat([latents] * 2), int(t))
+        latents = vpred_step_ref(latents, noise_pred, torch.as_tensor(alpha(int(t))), torch.as_tensor(alpha(int(t) - skip)), guidance_scale)[0]
+    return latents

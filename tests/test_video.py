@@ -65,6 +65,50 @@ def test_video_stepper_matches_reference_lines(monkeypatch, golden_dir):
         torch.testing.assert_close(got, rec["latents_out"], atol=5e-6, rtol=0)
 
 
+def _stub_unet_forward(model, dtype):
+    """A U-Net-shaped callable over the stub's hooked blocks: [2, C, 16, H, W] latents -> v-prediction of the same shape, every hooked
+    ResNet on the way (mid_block.resnets[0, 1], up_blocks[1].resnets[0, 1]), so the injection window changes the trajectory."""
+    u = model.unet
+
+    def fwd(x5, t):
+        b, c, f, h, w = x5.shape
+        x = x5.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+        temb = torch.sin(float(t) * 0.01 * torch.arange(1, 33, dtype=torch.float32)).to(x.device, dtype)[None].expand(b * f, -1)
+        y = u.mid_block.resnets[1].forward(u.mid_block.resnets[0].forward(x, temb), temb)
+        y = u.up_blocks[1].resnets[0].forward(torch.cat([y, x], 1), temb)
+        y = u.up_blocks[1].resnets[1].forward(y, temb)
+        return (0.5 * y).reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
+    return fwd
+
+
+def _loop_pair(gd_inject, gd_step, device, dtype, n_steps=10, ref_rounding=False):
+    """Product loop (product hooks + VideoStepper.denoise_loop) and oracle loop (oracle/video_ref.video_loop_ref) on two copies of the stub."""
+    from tweediemix_b200.video_gen.pipeline_step import VideoStepper
+    ac = gd_step["alphas_cumprod"]
+    ts = list(range(1000 - 1000 // n_steps + 1, 0, -(1000 // n_steps)))              # leading spacing, offset 1: 901, 801, ... 1
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(1, 16, 16, 6, 5, generator=g)
+    prod, orac = _model(gd_inject, device, dtype), _model(gd_inject, "cpu", torch.float32)
+    st = VideoStepper(ac, float(ac[0]), ts, 9.0, injection_timestep=0.25, ref_rounding=ref_rounding)
+    assert st.injection_schedule == ts[:2]
+    seen = []
+    got = st.denoise_loop(prod, lat.to(device, dtype), _stub_unet_forward(prod, dtype), interp_ratio=0.7, callback=lambda i, t, x: seen.append(t))
+    want = V.video_loop_ref(orac, lat, _stub_unet_forward(orac, torch.float32), ac, ac[0], ts, 9.0, 0.25, 0.7)
+    assert seen == ts and [m.t for m in (prod.unet.mid_block.resnets[0], prod.unet.up_blocks[1].resnets[1])] == [1, 1]
+    # and the window matters: the same loop without injection lands elsewhere
+    none = V.video_loop_ref(_model(gd_inject, "cpu", torch.float32), lat, _stub_unet_forward(_model(gd_inject, "cpu", torch.float32), torch.float32), ac, ac[0], ts, 9.0, 0.0, 0.7)
+    return got.float().cpu(), want, none
+
+
+@torch.no_grad()
+def test_video_denoise_loop_matches_oracle_loop(monkeypatch, golden_dir):
+    """pipeline_i2vgen_xl.py:655-656,677-719 as one call: hooks installed for the window, register_time per step, CFG halves, fused step."""
+    fake_ops.install(monkeypatch)
+    got, want, none = _loop_pair(_load(golden_dir, "video_inject.pt"), _load(golden_dir, "video_step.pt"), "cpu", torch.float32)
+    torch.testing.assert_close(got, want, atol=2e-4, rtol=0)
+    assert (want - none).abs().max() > 1e-2
+
+
 # ----------------------------------------------------------------------------------------- GPU
 def _ops():
     from tweediemix_b200 import build, ops
@@ -139,3 +183,16 @@ def test_product_video_hooks_match_reference_gpu(golden_dir):
     _ops()
     gd = _load(golden_dir, "video_inject.pt")
     _check_hooks(gd, _model(gd, "cuda", torch.float16), "cuda", torch.float16, 2e-2)
+
+
+@pytest.mark.gpu
+@torch.no_grad()
+def test_video_denoise_loop_matches_oracle_loop_gpu(golden_dir):
+    """The loop on the real k11 / k12 kernels (fp16 U-Net stand-in on CUDA) against the fp32 oracle loop: 10 chained steps stay within
+    fp16 rounding of the blocks' outputs (|latent| ~ 1)."""
+    _ops()
+    got, want, none = _loop_pair(_load(golden_dir, "video_inject.pt"), _load(golden_dir, "video_step.pt"), "cuda", torch.float16)
+    assert torch.isfinite(got).all()
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() <= 3e-2 * scale, ((got - want).abs().max().item(), scale)
+    assert (want - none).abs().max() > 1e-2

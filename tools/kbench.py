@@ -211,9 +211,10 @@ def main():
         import torch.nn.functional as F
         from tweediemix_b200 import _lib
         lib = _lib.load()
-        sites = [("qkv", 4096, 3840, 1280, "", 60), ("out|q", 4096, 1280, 1280, "res", 180), ("ff1", 4096, 10240, 1280, "geglu", 60),
-                 ("ff2", 4096, 1280, 5120, "res", 60), ("qkv", 16384, 1920, 640, "", 10), ("out|q", 16384, 640, 640, "res", 30),
-                 ("ff1", 16384, 5120, 640, "geglu", 10), ("ff2", 16384, 640, 2560, "res", 10)]
+        m32, m64 = B * 1024, B * 4096          # tokens of the 32x32 / 64x64 feature maps over the B rows this GPU holds
+        sites = [("qkv", m32, 3840, 1280, "", 60), ("out|q", m32, 1280, 1280, "res", 180), ("ff1", m32, 10240, 1280, "geglu", 60),
+                 ("ff2", m32, 1280, 5120, "res", 60), ("qkv", m64, 1920, 640, "", 10), ("out|q", m64, 640, 640, "res", 30),
+                 ("ff1", m64, 5120, 640, "geglu", 10), ("ff2", m64, 640, 2560, "res", 10)]
         for name, M, N, K, epi, cnt in sites:
             tag = f"{name}_M{M}_N{N}_K{K}"
             if not keep(tag):

@@ -1,6 +1,7 @@
 """The denoising-step arithmetic TweedieMix puts into ``I2VGenXLPipeline.__call__`` (``video_gen/pipeline_i2vgen_xl.py:647-656,679-719``):
 schedule helpers (``skip = 1000 // n``, un-shifted ``alpha(t)`` with ``final_alpha_cumprod`` below zero, the injection window = the first
-``int(n * injection_timestep)`` timesteps) and the fused CFG + v-prediction Tweedie + DDIM update (``tmx_vpred_cfg_ddim_fwd``)."""
+``int(n * injection_timestep)`` timesteps), the fused CFG + v-prediction Tweedie + DDIM update (``tmx_vpred_cfg_ddim_fwd``) and the
+denoising loop itself (``:655-656,677-719``) around any U-Net callable."""
 from __future__ import annotations
 
 from typing import Sequence
@@ -34,3 +35,20 @@ class VideoStepper:
         v_u, v_c = noise_pred[:B], noise_pred[B:]
         return ops.vpred_cfg_ddim(latents.contiguous(), v_u.contiguous(), v_c.contiguous(), self.alpha(int(t)), self.alpha(int(t) - self.skip),
                                   self.guidance_scale, out=out, ref_rounding=self.ref_rounding)
+
+    @torch.no_grad()
+    def denoise_loop(self, model, latents: torch.Tensor, unet_forward, interp_ratio: float = 0.7, callback=None) -> torch.Tensor:
+        """The reference's loop (``pipeline_i2vgen_xl.py:655-656,677-719``) around ``unet_forward(latent_model_input, t) -> v-prediction``:
+        installs the frame-0 injection hooks for this run's window, then per timestep stamps ``t`` on the hooked blocks
+        (``register_time``), feeds both CFG halves of the latents (``torch.cat([latents] * 2)``; DDIM's ``scale_model_input`` is the
+        identity) and takes the fused guidance + Tweedie + DDIM step.  ``model`` is whatever carries ``.unet`` (the pipeline object in the
+        reference); the U-Net itself — the I2VGen-XL model of diffusers, or a stand-in — is the caller's."""
+        from .utils_attn import register_conv_control_efficient, register_time
+        register_conv_control_efficient(model, self.injection_schedule, interp_ratio)                 # :655-656
+        for i, t in enumerate(self.timesteps):
+            register_time(model, t)                                                                    # :683
+            noise_pred = unet_forward(torch.cat([latents] * 2), t)                                     # :681-696
+            latents = self.step(latents, noise_pred, t)                                                # :698-713
+            if callback is not None:
+                callback(i, t, latents)
+        return latents
