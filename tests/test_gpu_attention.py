@@ -100,6 +100,35 @@ def test_attention_split_schedule(shape, sched, dtype):
     assert err <= ATOL[dtype], f"max|diff| {err}"
 
 
+SHORT_KV_SHAPES = [(4, 20, 1024, 77), (4, 10, 4096, 77), (1, 2, 200, 77), (2, 3, 130, 65), (1, 1, 64, 80), (1, 2, 100, 30), (1, 1, 50, 128), (3, 5, 257, 1)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("path", [30, 31, 32, 33])   # k1 (long-K/V tcgen05 kernel) / k2s streaming, 16 rows / k2s, 32 rows / k2t (tcgen05, 64 < Nk <= 80; else k2s)
+@pytest.mark.parametrize("shape", SHORT_KV_SHAPES)
+def test_attention_short_kv_paths(shape, path, dtype):
+    """Cross-attention shapes (<= 128 keys) through every kernel that can serve them; strided K/V (column slices of one fused
+    [B, Nk, 2*H*64] projection, as the hooks hand them over) and a second launch bit-identical to the first."""
+    o = ops()
+    from tweediemix_b200 import _lib
+    B, H, Nq, Nk = shape
+    g = torch.Generator().manual_seed(Nq + 7 * Nk + H)
+    q = torch.randn(B, Nq, H * 64, generator=g).to(dtype).cuda()
+    kv = (1.5 * torch.randn(B, Nk, 2 * H * 64, generator=g)).to(dtype).cuda()
+    k, v = kv[..., :H * 64], kv[..., H * 64:]
+    _lib.load().tmx_attn_set_variant(path)
+    try:
+        got = o.attention(q, k, v, H)
+        again = o.attention(q, k, v, H)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().tmx_attn_set_variant(0)
+    want = _ref(q, k.contiguous(), v.contiguous(), H)
+    assert torch.isfinite(got.float()).all() and torch.equal(got, again)
+    err = (got.float() - want).abs().max().item()
+    assert err <= ATOL[dtype], f"max|diff| {err}"
+
+
 def test_attention_large_logits_and_strided_qkv():
     """Peaked softmax (|logit| ~ 60: exercises the running-max / lazy-rescale path) and q/k/v given as
     column slices of one fused [B, N, 3*H*64] projection output (token stride 3*H*64)."""

@@ -17,7 +17,7 @@ def main():
     worst = 0.0
     # the B = 1 and ragged shapes cut units along K/V into 2-4 pieces (stream-K merge path), 300 rows = an odd tile count (lone last tile)
     for B, H, Nq, Nk in [(2, 10, 4096, 4096), (4, 20, 1024, 1024), (2, 20, 1024, 77), (1, 5, 200, 333), (1, 20, 1024, 1024), (1, 10, 4096, 4096),
-                         (1, 3, 300, 700), (2, 2, 128, 2000), (2, 20, 1024, 1024)]:
+                         (1, 3, 300, 700), (2, 2, 128, 2000), (2, 20, 1024, 1024), (4, 20, 1024, 77), (4, 10, 4096, 77), (1, 3, 200, 77), (2, 5, 130, 65), (1, 2, 64, 80)]:
         for dt in (torch.bfloat16, torch.float16):
             q, k, v_ = (torch.randn(B, n, H * 64, generator=g).to(dt).cuda() for n in (Nq, Nk, Nk))
             o = ops.attention(q, k, v_, H)

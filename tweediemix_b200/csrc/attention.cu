@@ -959,8 +959,8 @@ static int g_variant = 0;   // test hook: 0 / 2 = pair query tiles (default), 1 
 #define TMX_ATTN_HALVES 1
 #endif
 static int g_halves = TMX_ATTN_HALVES;   // softmax threads per query row (1 or 2)
-static int g_short = 1;                  // K/V sequences of <= 128 rows (cross-attention) go to the streaming kernel of cross_attention.cu with
-                                         // g_short 16-row tiles per warp iteration; 0 = keep them on the tcgen05 kernel (test hook: 30 / 31 / 32)
+static int g_short = 3;                  // K/V sequences of <= 128 rows (cross-attention) go to the streaming kernel of cross_attention.cu with
+                                         // g_short 16-row tiles per warp iteration (1, 2) or, with 3, to its tcgen05 kernel k2t; 0 = keep them on k1 (test hook: 30 .. 33)
 static int g_split = 1;                  // stream-K split of units along K/V between CTAs: 0 never, 1 by the cost model, 2 always (test hook: 20 / 21 / 22)
 
 }  // namespace tmx
@@ -974,13 +974,13 @@ extern "C" __attribute__((visibility("default"))) int tmx_attn_debug_trace(long 
 #endif
 
 extern "C" int tmx_attn_set_variant(int nq) {
-    // 0: defaults; 1: one query tile per step; 2: pairs; 11 / 12: 1 / 2 softmax threads per query row; 20 / 21 / 22: unit split never / by cost / always
+    // 0: defaults; 1: one query tile per step; 2: pairs; 11 / 12: 1 / 2 softmax threads per query row; 20 / 21 / 22: unit split never / by cost / always; 30 .. 33: short K/V on k1 / k2s / k2s 32 rows / k2t
     if (nq == 11 || nq == 12) { g_halves = nq - 10; return TMX_OK; }
     if (nq >= 20 && nq <= 22) { g_split = nq - 20; return TMX_OK; }
-    if (nq >= 30 && nq <= 32) { g_short = nq - 30; return TMX_OK; }
-    TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1, 2, 11, 12, 20, 21 or 22");
+    if (nq >= 30 && nq <= 33) { g_short = nq - 30; return TMX_OK; }
+    TMX_REQUIRE(nq >= 0 && nq <= 2, TMX_EINVAL, "attn_set_variant: nq must be 0, 1, 2, 11, 12, 20 .. 22 or 30 .. 33");
     g_variant = nq;
-    if (nq == 0) { g_halves = TMX_ATTN_HALVES; g_split = 1; g_short = 1; }
+    if (nq == 0) { g_halves = TMX_ATTN_HALVES; g_split = 1; g_short = 3; }
     return TMX_OK;
 }
 
