@@ -36,8 +36,8 @@ def main():
     print("# cuobjdump -sass tweediemix_b200/lib/libtmx.so (sm_100a): instruction evidence per kernel")
     print("# UTCHMMA = tcgen05.mma kind::f16, LDTM/STTM = tcgen05.ld/st (TMEM), UTMALDG/UTMASTG = cp.async.bulk.tensor load/store (TMA),")
     print("# UTCBAR = tcgen05.commit -> mbarrier, SYNCS = mbarrier ops, UCGABAR = cluster barrier, LDGSTS = cp.async, LDSM = ldmatrix.")
-    print("# HMMA (warp-level mma.sync) appears in exactly one kernel, by design: short_kv_attn_kernel, the streaming cross-attention")
-    print("# kernel for <= 128 keys (40 FLOP/B, HBM-bound; measured 20 % faster there than the tcgen05 kernel, profiles/r02q_*).")
+    print("# HMMA (warp-level mma.sync) appears in exactly one kernel family: short_kv_attn_kernel (k2s), the streaming alternative to the tcgen05 short-K/V kernel k2t")
+    print("# (short_kv_attn_tc_kernel, the default for the 77-token sites); k2s serves key counts k2t does not take (<= 64, 81..128).")
     print()
     for fn, c in counts.items():
         if total[fn] == 0:
