@@ -132,8 +132,9 @@ TMX_API int    tmx_groupnorm_fwd(const void* x, const float* gamma, const float*
                          void* y, void* workspace, int N, int C, int HW, int G, float eps,
                          int act, int layout, int dtype, void* stream);
 
-/* Tuning / test hook: 0 = fused single-launch path when applicable (default), 1 = always two launches,
- * 2 = fused kernel through a plain (non-cooperative) launch. */
+/* Tuning / test hook: 0 = defaults (one CTA or cluster per (sample, group) where that slab fits in shared memory, else the fused
+ * cooperative single launch where the activation fits in one wave of shared memory, else two launches), 1 = always two launches,
+ * 2 = fused kernel through a plain (non-cooperative) launch, 3 = per-group slab kernel off, 4 = on again, 5 = on without clusters. */
 TMX_API int tmx_groupnorm_set_variant(int v);
 
 /* Same as tmx_groupnorm_fwd (NHWC, 16-bit) over the channel concatenation [x1 | x2] WITHOUT materialising it: x1 is
@@ -188,13 +189,20 @@ TMX_API int tmx_geglu_fwd(const void* x, void* y, size_t rows, int F, int dtype,
  * projection output: *_stride_n >= H*64, multiple of 8; batch stride = N * stride_n.
  * dtype TMX_F16 or TMX_BF16.  Nq, Nk >= 1 (tails are masked).
  * Algorithmic FLOPs: 4 * B * H * Nq * Nk * 64.
+ *
+ * Three kernels behind this entry point: k1 (long K/V streams: persistent, stream-K scheduled over (query-tile pair, K/V tile)
+ * iterations — units cut along K/V between CTAs are merged through a per-device workspace allocated by tmx_init, so launches of
+ * ONE process on DIFFERENT streams of a device must not overlap), k2t (64 < Nk <= 80, the 77 text tokens of attn2: three query tiles
+ * in flight per SM) and k2s (other Nk <= 128: streaming warp-level kernel).
  */
 TMX_API int tmx_attn_fwd(const void* q, const void* k, const void* v, void* o,
                  int B, int H, int Nq, int Nk, int D,
                  int64_t q_stride_n, int64_t k_stride_n, int64_t v_stride_n, int64_t o_stride_n,
                  float scale, int dtype, void* stream);
 
-/* Tuning / test hook: force the number of 128-row query tiles per CTA (1 or 2); 0 = heuristic. */
+/* Tuning / test hook.  0 = defaults; 1 / 2 = one / two 128-row query tiles per step of k1 (and short K/V stays on k1);
+ * 11 / 12 = one / two softmax threads per row; 20 / 21 / 22 = units split along K/V between CTAs never / by the cost model / always;
+ * 30 .. 33 = short K/V (Nk <= 128) on k1 / k2s with 16 rows per warp / k2s with 32 rows / k2t where it applies (default). */
 TMX_API int tmx_attn_set_variant(int nq);
 
 /* ---------------------------------------------------------------------------------------------
