@@ -449,7 +449,9 @@ short_kv_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 const int g = kvi % kKvSlots;
                 mbar_wait(full + 8 * st, (uint32_t)(i / kStages) & 1u);
                 mbar_wait(kv_full + 8 * g, (uint32_t)(kvi / kKvSlots) & 1u);
-                if (i >= kSlots) mbar_wait(slot_free + 8 * j, ((uint32_t)(i / kSlots) - 1u) & 1u);
+                // the S / P columns of slot j are free as soon as P V of the slot's previous unit has completed (its o_full): the group
+                // may still be busy with that unit's epilogue — only the O columns are still in use, and those are the P V issuer's concern
+                if (i >= kSlots) mbar_wait(o_full + 8 * j, ((uint32_t)(i / kSlots) - 1u) & 1u);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t q_lo = desc_lo(s0 + st * kQBytes), k_lo = desc_lo(sKV + g * 2 * kKVBytes);
@@ -471,6 +473,7 @@ short_kv_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 const int g = kvi % kKvSlots;
                 const bool last_of_run = k + 1 >= n_units || (u_begin + k + 1) / QT != bh;
                 mbar_wait(p_full + 8 * j, (uint32_t)(k / kSlots) & 1u);
+                if (k >= kSlots) mbar_wait(slot_free + 8 * j, ((uint32_t)(k / kSlots) - 1u) & 1u);   // O of the slot's previous unit sits in registers
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t t_p = tmem_base + j * kSlotCols, t_o = t_p + 96;
@@ -540,7 +543,7 @@ short_kv_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(slot_free + 8 * slot);                              // S / P / O of this slot may be overwritten
+            if (lane == 0) mbar_arrive(slot_free + 8 * slot);                              // the O columns of this slot may be overwritten
 #pragma unroll
             for (int c = 0; c < kD; c += 8) {
                 uint4 v;
