@@ -13,7 +13,8 @@ from tweediemix_b200 import build, ops, _lib  # noqa: E402
 
 NAMES = {0: "tma  k_empty ok", 1: "tma  v_empty ok", 10: "mma  k_full(next) ok", 11: "mma  s_free ok", 12: "mma  QK issued",
          13: "pv   v_full ok", 16: "mma    4 QK MMAs issued", 17: "mma    commit 1 issued", 18: "mma    elected", 19: "mma    8 PV MMAs issued", 14: "pv   p_full ok", 15: "pv   PV issued", 20: "smx  s_full ok", 21: "smx  S loaded, s_free sent",
-         22: "smx  exp done (full tile)", 23: "smx  pv_done ok", 24: "smx  exp done", 25: "smx  P stored, p_full sent"}
+         22: "smx  exp done (full tile)", 23: "smx  pv_done ok", 24: "smx  exp done", 25: "smx  P stored, p_full sent",
+         30: "smx  EPILOGUE pv_done ok", 31: "smx  EPILOGUE barrier A passed", 32: "smx  EPILOGUE O staged, barrier B passed", 33: "smx  EPILOGUE store issued + read"}
 
 
 def main():
@@ -22,7 +23,8 @@ def main():
     count = int(sys.argv[3]) if len(sys.argv) > 3 else 90
     build.build()
     lib = _lib.load()
-    H, B = 10, 4
+    H = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+    B = int(sys.argv[5]) if len(sys.argv) > 5 else 4
     q = torch.randn(B, N, H * 64, device="cuda", dtype=torch.bfloat16)
     k = torch.randn_like(q); v = torch.randn_like(q)
     for _ in range(2):

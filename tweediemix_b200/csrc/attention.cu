@@ -836,6 +836,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             mbar_wait(bar_pv_done, (n - 1u) & 1u);
             tc_fence_after();
+            TMX_TRACE(30);
             if constexpr (HV == 1) {
                 if (cur.j0 > 0) {
                     // ---- partial piece of a unit owned by an earlier CTA: leave (O, m, l) un-normalised in this CTA's workspace
@@ -850,7 +851,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             // clipped by the tensor map.  Barrier A: the issuing thread has seen its previous store read the tile; barrier B: all rows written.
             const uint32_t o_row = sO_a + w * kTileBytes + row * 128;
             const uint32_t o_sw = (uint32_t)(row & 7);
+            // (the wait for the PREVIOUS store's shared-memory read sits here, a whole step after it was issued, not behind the issue:
+            // the event trace showed the issuing thread — and with it its whole slot — parked ~1700 clk per step on that wait)
+            if (half == 0 && quarter == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             asm volatile("bar.sync %0, %1;" :: "r"(11 + w), "n"(128 * HV) : "memory");
+            TMX_TRACE(31);
             int k_end = blockIdx.x + 1;                     // pieces [blockIdx.x + 1, k_end) were folded into this unit
 #ifndef TMX_SPLIT_NOMERGE
             if (HV == 1 && cur.j1 < T) {
@@ -879,18 +884,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, %1;" :: "r"(13 + w), "n"(128 * HV) : "memory");
+            TMX_TRACE(32);
             if (half == 0 && quarter == 0 && lane == 0) {
                 int cb, ch, cqt;
                 step_coords(cur.start, split, T, QT, UPP, TPU, H, cb, ch, cqt);
                 asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                              :: "l"(reinterpret_cast<uint64_t>(&tm_o)), "r"(sO_a + w * kTileBytes), "r"(0), "r"(ch), "r"((cqt + w) * kBM), "r"(cb) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 // every row of every piece has been read (barrier B): re-arm the pieces' flags for the next launch
 #ifndef TMX_SPLIT_NOWAIT
                 for (int k = blockIdx.x + 1; k < k_end; ++k) ws_flags[k * kSlots + w] = 0u;
 #endif
             }
+            TMX_TRACE(33);
             tc_fence_before();           // order the O reads before the next step's P(0) hand-off (p_full arrive)
         }
         if (half == 0 && quarter == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
