@@ -786,8 +786,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (c & 1) sum_b = fadd2(sum_b, pk2(e0, e1)); else sum_a = fadd2(sum_a, pk2(e0, e1));
                     packed = pack2<BF16>(e0, e1);
                 };
-                if (!pv_waited && j > cur.j0) {                                 // P(n-1) must have been consumed before it is overwritten;
-                    mbar_wait(bar_pv_done, (n - 1u) & 1u);                 // P V(n-1) was issued a whole load + max phase ago: normally ready
+                // P(n-1) must have been consumed by P V(n-1) before it is overwritten.  The event trace (profiles/r02z_*) shows 300-500 clk
+                // of this wait per tile; moving it behind the exp block, right in front of the store it protects, was measured SLOWER
+                // (227 vs 212 us at N = 4096: the poll loop in the middle of the block breaks up its MUFU / convert / store schedule).
+                if (!pv_waited && j > cur.j0) {
+                    mbar_wait(bar_pv_done, (n - 1u) & 1u);
                     tc_fence_after();
                 }
                 TMX_TRACE(23);
