@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU bench pass: bash tools/gpu_r02_nN.sh N  (the default run: configs[1] + the extra legs that N GPUs allow)
 N=${1:-4}
-OUT=gpurun_out/r02n$N
+OUT=gpurun_out/${2:-r02n$N}
 mkdir -p $OUT
 nvidia-smi --query-gpu=index,name --format=csv > $OUT/smi.txt 2>&1
 python -m tweediemix_b200.build > $OUT/build.log 2>&1
