@@ -21,9 +21,9 @@ def main(path):
         tot[name] += v
         cnt[name] += 1
     total = sum(tot.values())
-    ours = sum(v for n, v in tot.items() if "tmx::" in n)
+    ours = sum(v for n, v in tot.items() if any(ns in n for ns in ("tmx::", "k10::", "k3::", "xattn")))
     print(f"# {path}: {sum(cnt.values())} launches, {total:.1f} us serialised (cold-cache; compare shares, not absolutes)")
-    print(f"# hand-written tmx:: kernels: {ours:.1f} us = {100 * ours / total:.1f} % ; library (cuBLAS nvjet / cuDNN cutlass / ATen): {100 - 100 * ours / total:.1f} %")
+    print(f"# hand-written kernels (tmx:: / k10:: / k3:: / xattn*::): {ours:.1f} us = {100 * ours / total:.1f} % ; library (cuBLAS nvjet / cuDNN cutlass / ATen): {100 - 100 * ours / total:.1f} %")
     for n, v in tot.most_common():
         print(f"{v:10.1f} us {100 * v / total:5.1f}%  x{cnt[n]:4d}  {n}")
 
