@@ -22,6 +22,20 @@ namespace tmx {
 
 constexpr int kGnMaxParts = 1024;     // upper bound on partials per (n, group)
 constexpr int kGnMaxThreads = 512;
+// Rows in flight per thread and resident CTAs per SM of the two-launch kernels.  Measured (profiles/r02z_kbench_groupnorm_two_launch.txt):
+// at 2 CTAs per SM the 64-register cap spilled the row buffers of both kernels (72 / 36 bytes of spill stores inside the streaming
+// loops); ONE 480-512-thread CTA per SM with 8 rows (128 B) in flight per thread and no spills is 12-25 % faster at every site.
+#ifndef TMX_GN_U
+#define TMX_GN_U 8
+#endif
+#ifndef TMX_GN_US
+#define TMX_GN_US TMX_GN_U
+#endif
+constexpr int kGnU = TMX_GN_U;          // rows in flight per thread in the apply kernel of the two-launch path
+constexpr int kGnUS = TMX_GN_US;        // ... in the stats kernel (no output registers: more rows fit)
+#ifndef TMX_GN_MINB
+#define TMX_GN_MINB 1
+#endif
 
 template <typename T> struct V8 {
     static constexpr int kBytes = 16;
@@ -117,7 +131,7 @@ __device__ __forceinline__ void gn_cta_group_sums(float2* sh, const float (&S)[8
 // publishes stat[n*G+g] = (mean, rstd), so `apply` starts with two floats per group instead of
 // re-reducing the partials in every CTA.
 template <typename T>
-__global__ void __launch_bounds__(kGnMaxThreads, 2)
+__global__ void __launch_bounds__(kGnMaxThreads, TMX_GN_MINB)
 gn_stats_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const float* __restrict__ add, float2* __restrict__ part,
               float2* __restrict__ stat, unsigned int* __restrict__ tickets,
               int C, int HW, int G, int rows_per_cta, float eps) {
@@ -135,11 +149,11 @@ gn_stats_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
 
     // first batch of row loads goes out before anything else (the pivot staging below overlaps it)
     int r = row0 + ty;
-    uint4 q[4];
-    const bool full0 = (sizeof(T) == 2) && (r + 3 * RY < row1);
+    uint4 q[kGnUS];
+    const bool full0 = (sizeof(T) == 2) && (r + (kGnUS - 1) * RY < row1);
     if (full0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) q[u] = ld_keep(col + (size_t)(r + u * RY) * cs);
+        for (int u = 0; u < kGnUS; ++u) q[u] = ld_keep(col + (size_t)(r + u * RY) * cs);
     }
     // pivot = x'[n, pixel 0, first channel of the group]: sums of (x' - pivot) do not cancel
     for (int g = threadIdx.x; g < G; g += blockDim.x)
@@ -155,15 +169,15 @@ gn_stats_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
     if constexpr (sizeof(T) == 2) {
         if (full0) {
             while (true) {
-                const int rn = r + 4 * RY;
-                const bool more = rn + 3 * RY < row1;
-                uint4 qn[4];
+                const int rn = r + kGnUS * RY;
+                const bool more = rn + (kGnUS - 1) * RY < row1;
+                uint4 qn[kGnUS];
                 if (more) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) qn[u] = ld_keep(col + (size_t)(rn + u * RY) * cs);
+                    for (int u = 0; u < kGnUS; ++u) qn[u] = ld_keep(col + (size_t)(rn + u * RY) * cs);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kGnUS; ++u) {
                     float f[8];
                     unpack8<T>(q[u], f);
 #pragma unroll
@@ -172,7 +186,7 @@ gn_stats_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
                 r = rn;
                 if (!more) break;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) q[u] = qn[u];
+                for (int u = 0; u < kGnUS; ++u) q[u] = qn[u];
             }
         }
     }
@@ -208,7 +222,7 @@ gn_stats_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kGnMaxThreads, 2)
+__global__ void __launch_bounds__(kGnMaxThreads, TMX_GN_MINB)
 gn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ add, const float2* __restrict__ stat, T* __restrict__ y,
               int C, int HW, int G, int rows_per_cta, int act) {
@@ -221,11 +235,11 @@ gn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
     const size_t cs = src.cs;
     T* ycol = y + (size_t)n * HW * C + (size_t)tx * 8;
     int r = row0 + ty;
-    uint4 q[4];
-    const bool full0 = (sizeof(T) == 2) && (r + 3 * RY < row1);
+    uint4 q[kGnU];
+    const bool full0 = (sizeof(T) == 2) && (r + (kGnU - 1) * RY < row1);
     if (full0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) q[u] = ld_stream(col + (size_t)(r + u * RY) * cs);
+        for (int u = 0; u < kGnU; ++u) q[u] = ld_stream(col + (size_t)(r + u * RY) * cs);
     }
     float a[8], b[8];
 #pragma unroll
@@ -239,15 +253,15 @@ gn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
     if constexpr (sizeof(T) == 2) {
         if (full0) {
             while (true) {
-                const int rn = r + 4 * RY;
-                const bool more = rn + 3 * RY < row1;
-                uint4 qn[4];
+                const int rn = r + kGnU * RY;
+                const bool more = rn + (kGnU - 1) * RY < row1;
+                uint4 qn[kGnU];
                 if (more) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * cs);
+                    for (int u = 0; u < kGnU; ++u) qn[u] = ld_stream(col + (size_t)(rn + u * RY) * cs);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kGnU; ++u) {
                     float f[8];
                     unpack8<T>(q[u], f);
 #pragma unroll
@@ -260,7 +274,7 @@ gn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ x2, int C1, const f
                 r = rn;
                 if (!more) break;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) q[u] = qn[u];
+                for (int u = 0; u < kGnU; ++u) q[u] = qn[u];
             }
         }
     }
@@ -655,10 +669,10 @@ static GnPlan plan_nhwc(int N, int C, int HW) {
     const int CV = C / 8;
     p.RY = gn_row_lanes(CV);
     p.threads = CV * p.RY;
-    int want = (2 * sm_count() + N - 1) / N;                 // one resident wave: 2 CTAs per SM over the whole grid
+    int want = (TMX_GN_MINB * sm_count() + N - 1) / N;       // one resident wave: TMX_GN_MINB CTAs per SM over the whole grid
     if (want < 1) want = 1;
     int rows = (HW + want - 1) / want;
-    const int min_rows = 8 * p.RY;                           // >= 8 rows per thread when possible (two pipelined batches)
+    const int min_rows = 2 * (kGnU > kGnUS ? kGnU : kGnUS) * p.RY;                    // >= two pipelined batches of rows per thread when possible
     if (rows < min_rows) rows = min_rows;
     rows = ((rows + p.RY - 1) / p.RY) * p.RY;
     if (rows > HW) rows = HW;
