@@ -177,6 +177,18 @@ TMX_API int tmx_layernorm_fwd(const void* x, const float* gamma, const float* be
 TMX_API int tmx_geglu_fwd(const void* x, void* y, size_t rows, int F, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * k13 / k14 — the data-movement ops of the U-Net's up path on NHWC 16-bit tensors (bit-exact copies, 128-bit accesses):
+ *   tmx_cat_channels_fwd        y[r, 0:Ca] = a[r, :], y[r, Ca:Ca+Cb] = b[r, :] over rows = N*H*W pixels
+ *                               ([D] CrossAttnUpBlock2D / UpBlock2D: torch.cat([hidden_states, res_hidden_states], dim=1))
+ *   tmx_upsample_nearest2x_fwd  y[n, 2i+di, 2j+dj, :] = x[n, i, j, :]          x [N, H, W, C] -> y [N, 2H, 2W, C]
+ *                               ([D] Upsample2D: F.interpolate(scale_factor=2.0, mode="nearest"))
+ * Ca, Cb, C multiples of 8; dtype TMX_F16 or TMX_BF16; the output must not alias an input.
+ * Algorithmic bytes: 2 * rows * (Ca + Cb) * 2 (cat);  5 * N*H*W*C * 2 (upsample: 1 read + 4 writes).
+ */
+TMX_API int tmx_cat_channels_fwd(const void* a, const void* b, void* y, size_t rows, int Ca, int Cb, int dtype, void* stream);
+TMX_API int tmx_upsample_nearest2x_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * k1 / k2 — scaled-dot-product attention forward, head dim 64, no mask, non-causal:
  *   O[b,i,h,:] = softmax_j( scale * Q[b,i,h,:] . K[b,j,h,:] ) V[b,j,h,:]
  * tcgen05.mma (kind::f16) with fp32 accumulators in TMEM, operands staged by TMA.

@@ -96,6 +96,20 @@ def routed_linear(x, weights=None, lora_down=None, lora_up=None, *, nseg=1, out=
     return out
 
 
+def layout_supported(*ts):
+    return all(t.dim() == 4 and t.shape[1] % 8 == 0 for t in ts)
+
+
+def cat_channels(a, b, out=None):
+    y = torch.cat([a, b], dim=1)
+    return y if out is None else out.copy_(y)
+
+
+def upsample_nearest2x(x, out=None):
+    y = torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest")
+    return y if out is None else out.copy_(y)
+
+
 def cat_free_supported(a, b):
     return a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0
 
@@ -210,7 +224,7 @@ def blend_finish(x, acc, masks, a_t, a_next, g, *, is_last=False, out=None, x0_o
 
 NAMES = ("group_norm", "layer_norm", "residual_add", "bias_residual_add", "residual_add_layer_norm", "geglu", "attention",
          "tweedie_blend_ddim", "blend_partial", "blend_finish", "routed_linear", "linear", "lora_t", "linear_supported",
-         "vpred_cfg_ddim", "frame_inject", "cat_free_supported")
+         "vpred_cfg_ddim", "frame_inject", "cat_free_supported", "layout_supported", "cat_channels", "upsample_nearest2x")
 
 
 def install(monkeypatch):

@@ -429,3 +429,47 @@ def test_routed_linear_weights_plus_lora_and_errors():
     ptrs = (C.c_void_p * 17)(*[ws2[0].data_ptr()] * 17)
     rc = _lib.load().tmx_routed_linear_fwd(x2.data_ptr(), ptrs, None, None, x2.data_ptr(), 17, 4, 64, 24, 0, 1, _lib.BF16, None)
     assert rc == -2 and "B=17" in _lib.last_error()
+
+
+# ------------------------------------------------------------------------------------------ k13 / k14 (layout kernels)
+LAYOUT_CAT = [(4, 1280, 1280, 32, 32), (4, 1280, 640, 32, 32), (4, 640, 320, 64, 64), (4, 320, 320, 128, 128), (2, 640, 320, 128, 128),
+              (1, 8, 24, 3, 5), (3, 16, 8, 1, 1)]                                    # N, Ca, Cb, H, W: the SDXL up-block sites + ragged
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", LAYOUT_CAT)
+def test_cat_channels_is_torch_cat(dtype, shape):
+    """k13 == torch.cat([a, b], 1) bit for bit on channels_last tensors ([D] up blocks: torch.cat([hidden_states, res_hidden_states], dim=1))."""
+    o = ops()
+    N, Ca, Cb, H, W = shape
+    g = torch.Generator().manual_seed(Ca + Cb + H)
+    a = torch.randn(N, Ca, H, W, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    b = torch.randn(N, Cb, H, W, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    got = o.cat_channels(a, b)
+    assert got.shape == (N, Ca + Cb, H, W) and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, torch.cat([a, b], dim=1))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(4, 1280, 32, 32), (4, 640, 64, 64), (2, 320, 64, 64), (1, 8, 3, 5), (3, 24, 1, 1), (2, 16, 7, 1)])
+def test_upsample_nearest2x_is_interpolate(dtype, shape):
+    """k14 == F.interpolate(scale_factor=2, mode="nearest") bit for bit ([D] Upsample2D)."""
+    o = ops()
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    got = o.upsample_nearest2x(x)
+    want = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, want)
+
+
+def test_layout_kernels_errors():
+    o = ops()
+    a = torch.zeros(1, 12, 2, 2, dtype=torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)      # C % 8 != 0
+    assert not o.layout_supported(a)
+    with pytest.raises(RuntimeError, match="channels_last"):
+        o.cat_channels(a, a)
+    with pytest.raises(RuntimeError, match="channels_last"):
+        o.upsample_nearest2x(torch.zeros(1, 8, 2, 2, dtype=torch.bfloat16).cuda())                               # NCHW-dense, H*W > 1
+    x32 = torch.zeros(1, 8, 2, 2).cuda().contiguous(memory_format=torch.channels_last)
+    assert not o.layout_supported(x32)

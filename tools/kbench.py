@@ -160,6 +160,37 @@ def main():
             us = timeit(lambda i: ops.attention(q[i], k[i], v[i], H, out=o[i]), nb, args.reps)
             fl = 4.0 * B * H * N * Nk * 64
             out.append(("attention", f"Nq{N}_Nk{Nk}_H{H} x{cnt}", us, fl / us / 1e6, "TFLOP/s", tf))
+    if want("layout"):
+        # k13 / k14 at the up-path sites of one forward, with the ATen kernels they replace under --compare
+        import torch.nn.functional as F
+        for Ca, Cb, hw, cnt in [(1280, 1280, 32, 2), (1280, 640, 32, 1), (1280, 640, 64, 1), (640, 640, 64, 1), (640, 320, 64, 1),
+                                (640, 320, 128, 1), (320, 320, 128, 2)]:
+            tag = f"cat_C{Ca}+{Cb}_HW{hw * hw}"
+            if not keep(tag):
+                continue
+            nb = nbuf_for(2 * B * (Ca + Cb) * hw * hw * 2)
+            mk = lambda c: torch.randn(B, c, hw, hw, device=dev, dtype=DT).contiguous(memory_format=torch.channels_last)
+            as_, bs = [mk(Ca) for _ in range(nb)], [mk(Cb) for _ in range(nb)]
+            ys = [torch.empty(B, Ca + Cb, hw, hw, device=dev, dtype=DT).contiguous(memory_format=torch.channels_last) for _ in range(nb)]
+            nbytes = 2 * B * (Ca + Cb) * hw * hw * 2
+            us = timeit(lambda i: ops.cat_channels(as_[i], bs[i], out=ys[i]), nb, args.reps)
+            out.append(("layout", f"{tag} x{cnt}", us, nbytes / us / 1e3, "GB/s", hbm))
+            if args.compare:
+                us = timeit(lambda i: torch.cat([as_[i], bs[i]], dim=1, out=ys[i]), nb, args.reps)
+                out.append(("cmp:aten", f"torch.cat {tag} x{cnt}", us, nbytes / us / 1e3, "GB/s", hbm))
+        for Cc, hw, cnt in [(1280, 32, 1), (640, 64, 1)]:
+            tag = f"upsample_C{Cc}_HW{hw * hw}"
+            if not keep(tag):
+                continue
+            nb = nbuf_for(5 * B * Cc * hw * hw * 2)
+            xs = [torch.randn(B, Cc, hw, hw, device=dev, dtype=DT).contiguous(memory_format=torch.channels_last) for _ in range(nb)]
+            ys = [torch.empty(B, Cc, 2 * hw, 2 * hw, device=dev, dtype=DT).contiguous(memory_format=torch.channels_last) for _ in range(nb)]
+            nbytes = 5 * B * Cc * hw * hw * 2
+            us = timeit(lambda i: ops.upsample_nearest2x(xs[i], out=ys[i]), nb, args.reps)
+            out.append(("layout", f"{tag} x{cnt}", us, nbytes / us / 1e3, "GB/s", hbm))
+            if args.compare:
+                us = timeit(lambda i: F.interpolate(xs[i], scale_factor=2.0, mode="nearest"), nb, args.reps)
+                out.append(("cmp:aten", f"F.interpolate nearest {tag} x{cnt}", us, nbytes / us / 1e3, "GB/s", hbm))
     if want("blend"):
         for imgs in (1, 2048):
             if not keep(f"imgs{imgs}"):

@@ -57,6 +57,11 @@ def main():
     ops.residual_add_layer_norm(x.clone(), x, torch.ones(64, device=dev), torch.zeros(64, device=dev), 1e-5)
     ops.residual_add(x, x)
     ops.geglu(rnd(7, 3, 48).to(bf))
+    # k13 / k14: channel concat and nearest 2x upsample (NHWC)
+    ca = rnd(2, 8, 3, 5).to(bf).contiguous(memory_format=torch.channels_last)
+    cb = rnd(2, 24, 3, 5).to(bf).contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ops.cat_channels(ca, cb), torch.cat([ca, cb], 1))
+    assert torch.equal(ops.upsample_nearest2x(cb), torch.nn.functional.interpolate(cb, scale_factor=2.0, mode="nearest"))
     # k7 and its sharded halves
     xl = rnd(2, 4, 8, 8)
     eps = rnd(2, 4, 4, 8, 8).to(bf)

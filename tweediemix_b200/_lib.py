@@ -36,6 +36,8 @@ SIGNATURES = {
     "tmx_groupnorm_cat_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "tmx_groupnorm_launches": (_i, [_i, _i, _i, _i, _i]),
     "tmx_resadd_fwd": (_i, [_vp, _vp, _vp, _sz, _f, _i, _vp]),
+    "tmx_cat_channels_fwd": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
+    "tmx_upsample_nearest2x_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "tmx_bias_resadd_fwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),
     "tmx_resadd_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),
     "tmx_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),

@@ -277,6 +277,43 @@ def residual_add(a, b, inv_scale: float = 1.0, out=None):
     return out
 
 
+def layout_supported(*ts) -> bool:
+    """4-D channels_last CUDA fp16 / bf16 tensors of one dtype whose channel counts are multiples of 8 (k13 / k14)."""
+    return all(t.is_cuda and t.dim() == 4 and t.dtype in (torch.float16, torch.bfloat16) and t.dtype == ts[0].dtype and t.shape[1] % 8 == 0
+               and t.is_contiguous(memory_format=torch.channels_last) for t in ts)
+
+
+def cat_channels(a, b, out=None):
+    """torch.cat([a, b], dim=1) of two channels_last 16-bit feature maps ([D] up-block `torch.cat([hidden_states, res_hidden_states], 1)`)."""
+    _dev(a, b, out)
+    if not layout_supported(a, b) or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise RuntimeError("tmx.cat_channels: inputs must be channels_last fp16 / bf16 [N, C, H, W] with C % 8 == 0 and equal N, H, W")
+    N, Ca, H, W = a.shape
+    Cb = b.shape[1]
+    if out is None:
+        out = torch.empty((N, Ca + Cb, H, W), dtype=a.dtype, device=a.device, memory_format=torch.channels_last)
+    assert out.shape == (N, Ca + Cb, H, W) and out.dtype == a.dtype and out.is_contiguous(memory_format=torch.channels_last)
+    with _Launch("cat", 1, f"C{Ca}+{Cb}_HW{H * W}", 2.0 * N * H * W * (Ca + Cb) * a.element_size()):
+        rc = _lib.load().tmx_cat_channels_fwd(_p(a), _p(b), _p(out), N * H * W, Ca, Cb, _dt(a), _stream())
+    _lib.check(rc, "tmx_cat_channels_fwd")
+    return out
+
+
+def upsample_nearest2x(x, out=None):
+    """F.interpolate(x, scale_factor=2.0, mode="nearest") of a channels_last 16-bit feature map ([D] Upsample2D)."""
+    _dev(x, out)
+    if not layout_supported(x):
+        raise RuntimeError("tmx.upsample_nearest2x: input must be channels_last fp16 / bf16 [N, C, H, W] with C % 8 == 0")
+    N, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty((N, Cc, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    assert out.shape == (N, Cc, 2 * H, 2 * W) and out.dtype == x.dtype and out.is_contiguous(memory_format=torch.channels_last)
+    with _Launch("upsample", 1, f"C{Cc}_HW{H * W}", 5.0 * x.numel() * x.element_size()):
+        rc = _lib.load().tmx_upsample_nearest2x_fwd(_p(x), _p(out), N, H, W, Cc, _dt(x), _stream())
+    _lib.check(rc, "tmx_upsample_nearest2x_fwd")
+    return out
+
+
 def bias_residual_add(a, bias, b=None, inv_scale: float = 1.0, out=None):
     """(a + bias[c] (+ b)) * inv_scale on channels_last 4-D (or [..., C] dense) 16-bit tensors; bias fp32 [C]."""
     _dev(a, b, bias, out)

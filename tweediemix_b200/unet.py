@@ -541,7 +541,8 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
     def forward(self, x):
-        return _conv_bias(self.conv, F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        up = ops.upsample_nearest2x(x) if ops.layout_supported(x) else F.interpolate(x, scale_factor=2.0, mode="nearest")
+        return _conv_bias(self.conv, up)
 
 
 class DownBlock(nn.Module):
@@ -598,7 +599,7 @@ class UpBlock(nn.Module):
             if CAT_FREE and res.conv_shortcut is not None and ops.cat_free_supported(h, skip):
                 h = res(h, temb_all, x2=skip)                                 # no torch.cat: 9 copies of up to 126 MB per forward
             else:
-                h = res(torch.cat([h, skip], dim=1), temb_all)
+                h = res(ops.cat_channels(h, skip) if ops.layout_supported(h, skip) else torch.cat([h, skip], dim=1), temb_all)
             if self.attentions is not None:
                 h = self.attentions[i](h, ehs)
         if self.upsamplers is not None:
