@@ -59,13 +59,18 @@ bias_resadd_kernel(const T* __restrict__ a, const T* __restrict__ b, const float
 // BasicTransformerBlock fused with the LayerNorm that consumes its result.  One warp per row, the row
 // stays in registers: 2 reads + 2 writes instead of (2R + 1W) + (1R + 1W) and one launch instead of two.
 // The statistics are taken from the ROUNDED h, i.e. exactly the tensor the un-fused LayerNorm would read.
+#ifndef TMX_RLN_WARPS
+#define TMX_RLN_WARPS 2
+#endif
+constexpr int kRlnWarps = TMX_RLN_WARPS;       // rows (= warps) per CTA.  Measured (profiles/r02z_kbench_resadd_ln_cta_size.txt): 2-warp CTAs (16 resident
+                                               // per SM) balance the 4096-row sites over 148 SMs better than 8-warp ones: 10.1 -> 9.3 us at D = 1280
 template <typename T, int NV>
-__global__ void __launch_bounds__(256, 4)      // 4 CTAs / SM = 592 resident CTAs: the 512 CTAs of a 4 x 1024-token site run as ONE wave (60 registers, no spills)
+__global__ void __launch_bounds__(32 * kRlnWarps, 32 / kRlnWarps)      // 32 resident warps / SM: the CTAs of a 4 x 1024-token site run as ONE wave (60 registers, no spills)
 resadd_layernorm_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ gamma,
                         const float* __restrict__ beta, T* __restrict__ h_out, T* __restrict__ n_out,
                         long long rows, int D, float eps) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long row = (long long)blockIdx.x * kRlnWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int nvec = D >> 3;
     const T* ar = a + row * (long long)D;
@@ -126,9 +131,9 @@ resadd_layernorm_kernel(const T* __restrict__ a, const T* __restrict__ b, const 
 template <typename T>
 static int launch_resadd_ln(const void* a, const void* b, const float* gamma, const float* beta, void* h, void* n,
                             long long rows, int D, float eps, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    const unsigned blocks = (unsigned)((rows + kRlnWarps - 1) / kRlnWarps);
     const int nv = (D / 8 + 31) / 32;
-#define TMX_RLN(NVV) resadd_layernorm_kernel<T, NVV><<<blocks, 256, 0, st>>>((const T*)a, (const T*)b, gamma, beta, (T*)h, (T*)n, rows, D, eps)
+#define TMX_RLN(NVV) resadd_layernorm_kernel<T, NVV><<<blocks, 32 * kRlnWarps, 0, st>>>((const T*)a, (const T*)b, gamma, beta, (T*)h, (T*)n, rows, D, eps)
     switch (nv) {
         case 1: TMX_RLN(1); break;
         case 2: TMX_RLN(2); break;
@@ -175,7 +180,7 @@ extern "C" int tmx_resadd_layernorm_fwd(const void* a, const void* b, const floa
     TMX_REQUIRE(a && b && gamma && beta && h_out && n_out, TMX_EINVAL, "resadd_layernorm: null pointer");
     TMX_REQUIRE(rows > 0 && D > 0, TMX_EINVAL, "resadd_layernorm: non-positive size");
     TMX_REQUIRE(D % 8 == 0 && D <= 2048, TMX_ESHAPE, "resadd_layernorm: D=%d must be a multiple of 8 and <= 2048", D);
-    TMX_REQUIRE(rows <= 0x7fffffffULL * 8ULL, TMX_ESHAPE, "resadd_layernorm: too many rows");
+    TMX_REQUIRE(rows <= 0x7fffffffULL * (unsigned long long)kRlnWarps, TMX_ESHAPE, "resadd_layernorm: too many rows");
     TMX_REQUIRE(aligned16(a) && aligned16(b) && aligned16(h_out) && aligned16(n_out) && aligned16(gamma) && aligned16(beta),
                 TMX_EALIGN, "resadd_layernorm: 16-byte alignment");
     TMX_REQUIRE(n_out != a && n_out != b && n_out != h_out, TMX_EINVAL, "resadd_layernorm: n_out must not alias the other buffers");
