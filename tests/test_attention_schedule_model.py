@@ -143,3 +143,54 @@ def test_one_kv_tile_never_splits_and_grid_never_exceeds_units():
         for mode in (1, 2):
             p = check_schedule(*shape, split_mode=mode)
             assert p["split"] == 0
+
+
+# ------------------------------------------------------------------------------------------------ merge arithmetic (split_merge)
+def _piece(q, k, v, j0, j1, scale_log2, thr=8.0, dtype=None):
+    """One piece of a unit as the softmax warps compute it: K/V tiles [j0, j1), lazy reference maximum (moved only when the tile
+    maximum exceeds it by more than `thr`), P rounded to the I/O dtype before P V, l accumulated in fp32 from the unrounded P.
+    Returns (O un-normalised, m_ref, l) per row."""
+    import torch
+    n = q.shape[0]
+    m = torch.full((n,), float("-inf"))
+    l = torch.zeros(n)
+    o = torch.zeros(n, v.shape[1])
+    for j in range(j0, j1):
+        s = (q @ k[j * KBN:(j + 1) * KBN].T) * scale_log2
+        mt = s.max(dim=1).values
+        bump = mt > m + thr
+        m_new = torch.where(bump, mt, m)
+        alpha = torch.where(bump, torch.exp2(m - m_new), torch.ones(n))
+        alpha = torch.where(torch.isinf(m), torch.zeros(n), alpha)
+        p = torch.exp2(s - m_new[:, None])
+        l = l * alpha + p.sum(dim=1)
+        pr = p.to(dtype).float() if dtype is not None else p
+        o = o * alpha[:, None] + pr @ v[j * KBN:(j + 1) * KBN]
+        m = m_new
+    return o, m, l
+
+
+@pytest.mark.parametrize("cuts", [(3,), (1, 2), (2, 5, 6), (1, 2, 3, 4, 5, 6, 7)])
+def test_merging_pieces_equals_the_whole_softmax(cuts):
+    """The owner's fold (split_merge: m_new = max, O = O * 2^(m - m_new) + O_k * 2^(m_k - m_new), same for l, pieces in CTA order)
+    over un-normalised partials with DIFFERENT lazy reference maxima reproduces softmax(Q K^T) V."""
+    import torch
+    torch.manual_seed(0)
+    T, d = 8, 64
+    q = torch.randn(128, d)
+    k = torch.randn(T * KBN, d) * 2.0                       # peaked rows: the pieces see different maxima, some rescale, some do not
+    v = torch.randn(T * KBN, d)
+    sl2 = 0.125 * 1.4426950408889634
+    want = torch.softmax((q @ k.T) * 0.125, dim=1) @ v
+    for dtype, tol in ((None, 2e-5), (torch.bfloat16, 2e-2), (torch.float16, 3e-3)):
+        bounds = [0, *cuts, T]
+        o, m, l = _piece(q, k, v, bounds[0], bounds[1], sl2, dtype=dtype)            # the owner's head piece
+        for a, b in zip(bounds[1:-1], bounds[2:]):                                  # the following CTAs' pieces, in order
+            ok, mk, lk = _piece(q, k, v, a, b, sl2, dtype=dtype)
+            m_new = torch.maximum(m, mk)
+            a_own, a_k = torch.exp2(m - m_new), torch.exp2(mk - m_new)
+            l = l * a_own + lk * a_k
+            o = o * a_own[:, None] + ok * a_k[:, None]
+            m = m_new
+        got = o / l[:, None]
+        assert (got - want).abs().max().item() <= tol
